@@ -1,0 +1,386 @@
+// fx_capi.cu -- the C-ABI of libfxenv.so (include/fxenv.h): handle management, device memory, kernel launches.
+// No torch types, no exceptions across the boundary; every entry point returns a status code.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+#include <vector>
+
+#include "fx_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct SlabPlan {
+  size_t bytes = 0;
+  size_t add(size_t nbytes) {
+    const size_t off = bytes;
+    bytes += (nbytes + 255) & ~(size_t)255;
+    return off;
+  }
+};
+
+}  // namespace
+
+struct FxEnv {
+  FxKernelParams P;
+  int device = 0;
+  unsigned char* slab = nullptr;
+  size_t slab_bytes = 0;
+  double* candles_dev[FXENV_MAX_PAIRS] = {};
+  double* stats_dev[FXENV_MAX_PAIRS] = {};
+  int64_t* minutes_dev[FXENV_MAX_PAIRS] = {};
+  bool loaded[FXENV_MAX_PAIRS] = {};
+  bool was_reset = false;
+  bool first_reset = true;
+  int64_t launches = 0;
+  std::string err;
+  // fxenv_step_host staging
+  cudaStream_t hstream = nullptr;
+  void* h_actions = nullptr;
+  float* h_obs = nullptr;
+  float* h_reward = nullptr;
+  uint8_t* h_term = nullptr;
+  // fxenv_step_many graph cache (one entry: the last pointer set)
+  cudaGraphExec_t gexec = nullptr;
+  const void* g_actions = nullptr;
+  float* g_obs = nullptr;
+  float* g_reward = nullptr;
+  uint8_t* g_term = nullptr;
+  int g_steps = 0, g_slots = 0;
+};
+
+namespace {
+
+int fail(FxEnv* env, int code, const std::string& msg) {
+  if (env) env->err = msg; else g_create_error = msg;
+  return code;
+}
+
+int cuda_fail(FxEnv* env, cudaError_t e, const char* what) {
+  return fail(env, FXENV_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define FX_CUDA(env, call)                                   \
+  do {                                                       \
+    cudaError_t e__ = (call);                                \
+    if (e__ != cudaSuccess) return cuda_fail(env, e__, #call); \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev); else prev = -1;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int validate(const FxConfig& c, std::string& why) {
+  char buf[256];
+#define BAD(...) do { snprintf(buf, sizeof buf, __VA_ARGS__); why = buf; return FXENV_E_INVALID; } while (0)
+  if (c.struct_size != (int32_t)sizeof(FxConfig)) BAD("FxConfig.struct_size %d != %d (ABI mismatch)", c.struct_size, (int)sizeof(FxConfig));
+  if (c.num_envs < 1) BAD("num_envs must be >= 1");
+  if (c.num_pairs < 1 || c.num_pairs > FXENV_MAX_PAIRS) BAD("num_pairs must be in 1..%d", FXENV_MAX_PAIRS);
+  if (c.n_cols < 5 || c.n_cols > FXENV_MAX_COLS) BAD("n_cols must be in 5..%d", FXENV_MAX_COLS);
+  if (c.order_capacity < 0 || c.order_capacity > 512) BAD("order_capacity must be in 0..512");
+  if (c.window_size < 1) BAD("window_size must be >= 1");
+  if (c.price_col < 0 || c.price_col >= c.n_cols) BAD("price_col out of range");
+  if (c.slippage_perc != 0.0) BAD("slippage_perc != 0 is not supported yet");
+  if (!(c.leverage > 0.0)) BAD("leverage must be > 0");
+  if (c.strategy < 0 || c.strategy > FX_STRATEGY_ATR_SLTP) BAD("unknown strategy %d", c.strategy);
+  if (c.strategy == FX_STRATEGY_ATR_SLTP && (c.atr_period < 1 || c.atr_period > 64)) BAD("atr_period must be in 1..64");
+  if (c.strategy != FX_STRATEGY_DEFAULT && c.strat_position_size == 0.0 && !c.use_rel_volume) BAD("bracket strategies need position_size != 0");
+  if (c.preproc < 0 || c.preproc > FX_PREPROC_FEATURE_WINDOW) BAD("unknown preprocessor %d", c.preproc);
+  if (c.preproc == FX_PREPROC_FEATURE_WINDOW) {
+    if (c.n_features < 1 || c.n_features > FXENV_MAX_FEATURES) BAD("n_features must be in 1..%d", FXENV_MAX_FEATURES);
+    for (int i = 0; i < c.n_features; i++)
+      if (c.feature_cols[i] < 0 || c.feature_cols[i] >= c.n_cols) BAD("feature_cols[%d] out of range", i);
+    if (c.scaling < 0 || c.scaling > FX_SCALING_EXPANDING) BAD("unknown feature scaling %d", c.scaling);
+    if (c.scaling == FX_SCALING_ROLLING && c.scaling_window < 1) BAD("feature_scaling_window must be >= 1");
+  }
+  if (c.reward < 0 || c.reward > FX_REWARD_DD) BAD("unknown reward %d", c.reward);
+  if (c.reward == FX_REWARD_SHARPE && (c.sharpe_window < 1 || c.sharpe_window > 4096)) BAD("sharpe window must be in 1..4096");
+  if (c.reward_initial_cash == 0.0) BAD("reward_initial_cash must be non-zero (the reference substitutes 1.0)");
+  if (c.episode_bars < 0) BAD("episode_bars must be >= 0");
+#undef BAD
+  return FXENV_OK;
+}
+
+int require_ready(FxEnv* env, bool need_reset) {
+  if (!env) return FXENV_E_INVALID;
+  for (int p = 0; p < env->P.cfg.num_pairs; p++)
+    if (!env->loaded[p]) return fail(env, FXENV_E_STATE, "candles for pair " + std::to_string(p) + " not loaded");
+  if (need_reset && !env->was_reset) return fail(env, FXENV_E_STATE, "Call reset() before step().");
+  return FXENV_OK;
+}
+
+void drop_graph(FxEnv* env) {
+  if (env->gexec) { cudaGraphExecDestroy(env->gexec); env->gexec = nullptr; }
+}
+
+}  // namespace
+
+extern "C" {
+
+int fxenv_abi_version(void) { return FXENV_ABI_VERSION; }
+
+const char* fxenv_last_error(const FxEnv* env) { return env ? env->err.c_str() : g_create_error.c_str(); }
+
+int fxenv_create(const FxConfig* cfg, FxEnv** out) {
+  if (!cfg || !out) return fail(nullptr, FXENV_E_INVALID, "null argument");
+  *out = nullptr;
+  std::string why;
+  int rc = validate(*cfg, why);
+  if (rc != FXENV_OK) return fail(nullptr, rc, why);
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0)
+    return fail(nullptr, FXENV_E_CUDA, std::string("no CUDA device available (libfxenv has no CPU path): ") +
+                                           (ce != cudaSuccess ? cudaGetErrorString(ce) : "device count is 0"));
+  FxEnv* env = new (std::nothrow) FxEnv();
+  if (!env) return fail(nullptr, FXENV_E_NOMEM, "out of host memory");
+  memset(&env->P, 0, sizeof env->P);
+  env->P.cfg = *cfg;
+  FxConfig& c = env->P.cfg;
+  if (cudaGetDevice(&env->device) != cudaSuccess) { delete env; return fail(nullptr, FXENV_E_CUDA, "cudaGetDevice failed"); }
+  int cap = c.order_capacity == 0 ? 128 : c.order_capacity;
+  cap = (cap + 31) & ~31;
+  c.order_capacity = cap;
+  env->P.cap = cap;
+  env->P.obs_dim = (int32_t)fx_obs_dim(c);
+  env->P.smem_per_warp = (int32_t)fx_smem_per_warp(c, cap);
+  env->P.fast_features = 0;
+  if (c.preproc == FX_PREPROC_FEATURE_WINDOW && c.n_features == c.n_cols) {
+    env->P.fast_features = 1;
+    for (int i = 0; i < c.n_features; i++) if (c.feature_cols[i] != i) env->P.fast_features = 0;
+  }
+  // one slab for the whole per-env state (snapshot == one memcpy)
+  const size_t N = (size_t)c.num_envs;
+  const size_t ring = (c.reward == FX_REWARD_SHARPE) ? (size_t)c.sharpe_window : 1;
+  SlabPlan plan;
+  size_t o_d[9], o_start, o_i[10], o_flags, o_ring, o_meta, o_p0, o_p1, o_sz;
+  for (int i = 0; i < 9; i++) o_d[i] = plan.add(N * 8);
+  o_start = plan.add(N * 8);
+  for (int i = 0; i < 10; i++) o_i[i] = plan.add(N * 4);
+  o_flags = plan.add(N * 4);
+  o_ring = plan.add(N * ring * 8);
+  o_meta = plan.add(N * cap * 4);
+  o_p0 = plan.add(N * cap * 8);
+  o_p1 = plan.add(N * cap * 8);
+  o_sz = plan.add(N * cap * 8);
+  env->slab_bytes = plan.bytes;
+  ce = cudaMalloc(&env->slab, plan.bytes);
+  if (ce != cudaSuccess) { delete env; return cuda_fail(nullptr, ce, "cudaMalloc(state slab)"); }
+  cudaMemset(env->slab, 0, plan.bytes);
+  FxDeviceState& st = env->P.st;
+  unsigned char* b = env->slab;
+  double** dcols[9] = {&st.cash, &st.psize, &st.pprice, &st.value, &st.equity, &st.prev_equity, &st.price,
+                       &st.commission_paid, &st.dd_peak};
+  for (int i = 0; i < 9; i++) *dcols[i] = reinterpret_cast<double*>(b + o_d[i]);
+  st.start = reinterpret_cast<int64_t*>(b + o_start);
+  int32_t** icols[10] = {&st.t, &st.total_bars, &st.position, &st.bar_index, &st.trades, &st.n_orders,
+                         &st.sh_len, &st.sh_head, &st.sh_last_step, &st.dd_last_step};
+  for (int i = 0; i < 10; i++) *icols[i] = reinterpret_cast<int32_t*>(b + o_i[i]);
+  st.flags = reinterpret_cast<uint32_t*>(b + o_flags);
+  st.sh_ring = reinterpret_cast<double*>(b + o_ring);
+  st.o_meta = reinterpret_cast<uint32_t*>(b + o_meta);
+  st.o_p0 = reinterpret_cast<double*>(b + o_p0);
+  st.o_p1 = reinterpret_cast<double*>(b + o_p1);
+  st.o_sz = reinterpret_cast<double*>(b + o_sz);
+  *out = env;
+  return FXENV_OK;
+}
+
+int fxenv_destroy(FxEnv* env) {
+  if (!env) return FXENV_OK;
+  DeviceGuard g(env->device);
+  drop_graph(env);
+  for (int p = 0; p < FXENV_MAX_PAIRS; p++) {
+    cudaFree(env->candles_dev[p]); cudaFree(env->stats_dev[p]); cudaFree(env->minutes_dev[p]);
+  }
+  cudaFree(env->slab);
+  cudaFree(env->h_actions); cudaFree(env->h_obs); cudaFree(env->h_reward); cudaFree(env->h_term);
+  if (env->hstream) cudaStreamDestroy(env->hstream);
+  delete env;
+  return FXENV_OK;
+}
+
+int fxenv_load_candles(FxEnv* env, int pair_id, const double* candles_host, int64_t T, const int64_t* minutes_host) {
+  if (!env) return FXENV_E_INVALID;
+  const FxConfig& c = env->P.cfg;
+  if (pair_id < 0 || pair_id >= c.num_pairs) return fail(env, FXENV_E_INVALID, "pair_id out of range");
+  if (!candles_host) return fail(env, FXENV_E_INVALID, "candles_host is null");
+  // app/env.py:64-65: the data must be longer than the window
+  if (T < (int64_t)c.window_size + 2) return fail(env, FXENV_E_INVALID, "input data is empty or too short for the configured window");
+  DeviceGuard g(env->device);
+  drop_graph(env);
+  cudaFree(env->candles_dev[pair_id]); cudaFree(env->stats_dev[pair_id]); cudaFree(env->minutes_dev[pair_id]);
+  env->candles_dev[pair_id] = nullptr; env->stats_dev[pair_id] = nullptr; env->minutes_dev[pair_id] = nullptr;
+  env->loaded[pair_id] = false;
+  const size_t bytes = (size_t)T * c.n_cols * 8;
+  FX_CUDA(env, cudaMalloc(&env->candles_dev[pair_id], bytes));
+  FX_CUDA(env, cudaMemcpy(env->candles_dev[pair_id], candles_host, bytes, cudaMemcpyHostToDevice));
+  if (minutes_host) {
+    FX_CUDA(env, cudaMalloc(&env->minutes_dev[pair_id], (size_t)T * 8));
+    FX_CUDA(env, cudaMemcpy(env->minutes_dev[pair_id], minutes_host, (size_t)T * 8, cudaMemcpyHostToDevice));
+  }
+  if (c.preproc == FX_PREPROC_FEATURE_WINDOW && c.scaling == FX_SCALING_ROLLING) {
+    FX_CUDA(env, cudaMalloc(&env->stats_dev[pair_id], (size_t)T * c.n_features * 16));
+    FX_CUDA(env, fx_launch_stats(c, env->candles_dev[pair_id], env->stats_dev[pair_id], T, 0));
+    env->launches++;
+    FX_CUDA(env, cudaDeviceSynchronize());
+  }
+  FxPairTable& tb = env->P.pair[pair_id];
+  tb.candles = env->candles_dev[pair_id];
+  tb.stats = env->stats_dev[pair_id];
+  tb.minutes = env->minutes_dev[pair_id];
+  tb.T = T;
+  env->loaded[pair_id] = true;
+  return FXENV_OK;
+}
+
+int64_t fxenv_obs_dim(const FxEnv* env) { return env ? env->P.obs_dim : -1; }
+
+int fxenv_reset(FxEnv* env, const int64_t* start_bar_dev, const uint8_t* mask_dev, void* stream) {
+  int rc = require_ready(env, false);
+  if (rc) return rc;
+  DeviceGuard g(env->device);
+  FX_CUDA(env, fx_launch_reset(env->P, start_bar_dev, env->first_reset ? nullptr : mask_dev, env->first_reset ? 1 : 0,
+                               (cudaStream_t)stream));
+  env->launches++;
+  env->first_reset = false;
+  env->was_reset = true;
+  return FXENV_OK;
+}
+
+int fxenv_observe(FxEnv* env, float* obs_dev, void* stream) {
+  int rc = require_ready(env, true);
+  if (rc) return rc;
+  if (!obs_dev) return fail(env, FXENV_E_INVALID, "obs_dev is null");
+  DeviceGuard g(env->device);
+  FX_CUDA(env, fx_launch_observe(env->P, obs_dev, (cudaStream_t)stream));
+  env->launches++;
+  return FXENV_OK;
+}
+
+int fxenv_step(FxEnv* env, const void* actions_dev, float* obs_dev, float* reward_dev, uint8_t* terminated_dev,
+               double* reward64_dev, void* stream) {
+  int rc = require_ready(env, true);
+  if (rc) return rc;
+  if (!actions_dev || !obs_dev || !reward_dev || !terminated_dev) return fail(env, FXENV_E_INVALID, "null I/O pointer");
+  DeviceGuard g(env->device);
+  FX_CUDA(env, fx_launch_step(env->P, actions_dev, obs_dev, reward_dev, reward64_dev, terminated_dev, (cudaStream_t)stream));
+  env->launches++;
+  return FXENV_OK;
+}
+
+int fxenv_step_many(FxEnv* env, int n_steps, const void* actions_dev, float* obs_dev, int obs_slots, float* reward_dev,
+                    uint8_t* terminated_dev, void* stream_) {
+  int rc = require_ready(env, true);
+  if (rc) return rc;
+  if (n_steps < 1 || obs_slots < 1) return fail(env, FXENV_E_INVALID, "n_steps and obs_slots must be >= 1");
+  if (!actions_dev || !obs_dev || !reward_dev || !terminated_dev) return fail(env, FXENV_E_INVALID, "null I/O pointer");
+  DeviceGuard g(env->device);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const size_t N = (size_t)env->P.cfg.num_envs, D = (size_t)env->P.obs_dim;
+  auto enqueue = [&](cudaStream_t s) -> cudaError_t {
+    for (int k = 0; k < n_steps; k++) {
+      const char* a = reinterpret_cast<const char*>(actions_dev) + (size_t)k * N * 4;
+      cudaError_t e = fx_launch_step(env->P, a, obs_dev + (size_t)(k % obs_slots) * N * D, reward_dev + (size_t)k * N,
+                                     nullptr, terminated_dev + (size_t)k * N, s);
+      if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+  };
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (stream != nullptr) cudaStreamIsCapturing(stream, &cs);
+  if (cs != cudaStreamCaptureStatusNone || n_steps == 1 || stream == nullptr) {
+    // already inside someone else's capture (e.g. a torch CUDA graph), or nothing to amortise: plain launches
+    FX_CUDA(env, enqueue(stream));
+    env->launches += n_steps;
+    return FXENV_OK;
+  }
+  const bool hit = env->gexec && env->g_actions == actions_dev && env->g_obs == obs_dev && env->g_reward == reward_dev &&
+                   env->g_term == terminated_dev && env->g_steps == n_steps && env->g_slots == obs_slots;
+  if (!hit) {
+    drop_graph(env);
+    cudaGraph_t graph = nullptr;
+    FX_CUDA(env, cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+    cudaError_t e = enqueue(stream);
+    cudaError_t e2 = cudaStreamEndCapture(stream, &graph);
+    if (e != cudaSuccess) { if (graph) cudaGraphDestroy(graph); return cuda_fail(env, e, "capture: fx_launch_step"); }
+    if (e2 != cudaSuccess) return cuda_fail(env, e2, "cudaStreamEndCapture");
+    e = cudaGraphInstantiate(&env->gexec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { env->gexec = nullptr; return cuda_fail(env, e, "cudaGraphInstantiate"); }
+    env->g_actions = actions_dev; env->g_obs = obs_dev; env->g_reward = reward_dev; env->g_term = terminated_dev;
+    env->g_steps = n_steps; env->g_slots = obs_slots;
+  }
+  FX_CUDA(env, cudaGraphLaunch(env->gexec, stream));
+  env->launches += n_steps;
+  return FXENV_OK;
+}
+
+int fxenv_step_host(FxEnv* env, const void* actions_host, float* obs_host, float* reward_host, uint8_t* terminated_host) {
+  int rc = require_ready(env, true);
+  if (rc) return rc;
+  if (!actions_host || !obs_host || !reward_host || !terminated_host) return fail(env, FXENV_E_INVALID, "null I/O pointer");
+  DeviceGuard g(env->device);
+  const size_t N = (size_t)env->P.cfg.num_envs, D = (size_t)env->P.obs_dim;
+  if (!env->hstream) {
+    FX_CUDA(env, cudaStreamCreateWithFlags(&env->hstream, cudaStreamNonBlocking));
+    FX_CUDA(env, cudaMalloc(&env->h_actions, N * 4));
+    FX_CUDA(env, cudaMalloc(&env->h_obs, N * D * 4));
+    FX_CUDA(env, cudaMalloc(&env->h_reward, N * 4));
+    FX_CUDA(env, cudaMalloc(&env->h_term, N));
+  }
+  cudaStream_t s = env->hstream;
+  FX_CUDA(env, cudaMemcpyAsync(env->h_actions, actions_host, N * 4, cudaMemcpyHostToDevice, s));
+  FX_CUDA(env, fx_launch_step(env->P, env->h_actions, env->h_obs, env->h_reward, nullptr, env->h_term, s));
+  env->launches++;
+  FX_CUDA(env, cudaMemcpyAsync(obs_host, env->h_obs, N * D * 4, cudaMemcpyDeviceToHost, s));
+  FX_CUDA(env, cudaMemcpyAsync(reward_host, env->h_reward, N * 4, cudaMemcpyDeviceToHost, s));
+  FX_CUDA(env, cudaMemcpyAsync(terminated_host, env->h_term, N, cudaMemcpyDeviceToHost, s));
+  FX_CUDA(env, cudaStreamSynchronize(s));
+  return FXENV_OK;
+}
+
+int fxenv_get_info(FxEnv* env, FxInfoPtrs* out) {
+  if (!env || !out) return FXENV_E_INVALID;
+  const FxDeviceState& st = env->P.st;
+  out->equity = st.equity; out->prev_equity = st.prev_equity; out->price = st.price; out->cash = st.cash;
+  out->position_size = st.psize; out->position_price = st.pprice; out->commission_paid = st.commission_paid;
+  out->position = st.position; out->bar_index = st.bar_index; out->total_bars = st.total_bars;
+  out->trades = st.trades; out->n_orders = st.n_orders; out->flags = st.flags;
+  return FXENV_OK;
+}
+
+int64_t fxenv_state_bytes(const FxEnv* env) { return env ? (int64_t)env->slab_bytes : -1; }
+
+int fxenv_get_state(FxEnv* env, void* buf_host, int64_t nbytes) {
+  if (!env || !buf_host) return FXENV_E_INVALID;
+  if (nbytes != (int64_t)env->slab_bytes) return fail(env, FXENV_E_INVALID, "state buffer size mismatch");
+  DeviceGuard g(env->device);
+  FX_CUDA(env, cudaDeviceSynchronize());
+  FX_CUDA(env, cudaMemcpy(buf_host, env->slab, env->slab_bytes, cudaMemcpyDeviceToHost));
+  return FXENV_OK;
+}
+
+int fxenv_set_state(FxEnv* env, const void* buf_host, int64_t nbytes) {
+  if (!env || !buf_host) return FXENV_E_INVALID;
+  if (nbytes != (int64_t)env->slab_bytes) return fail(env, FXENV_E_INVALID, "state buffer size mismatch");
+  DeviceGuard g(env->device);
+  FX_CUDA(env, cudaDeviceSynchronize());
+  FX_CUDA(env, cudaMemcpy(env->slab, buf_host, env->slab_bytes, cudaMemcpyHostToDevice));
+  env->was_reset = true;
+  env->first_reset = false;
+  return FXENV_OK;
+}
+
+int64_t fxenv_launch_count(const FxEnv* env) { return env ? env->launches : -1; }
+
+}  // extern "C"
