@@ -1,0 +1,319 @@
+#!/usr/bin/env python3
+"""
+bench.py -- env-steps/sec of the gym-fx env.step() hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3|cfg4|cfg5]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" = one env.step() of every env of the workload (one launch of the fused kernel per GPU).  Default
+workload = BASELINE configs[1]: 4096 envs/GPU, feature_window_preprocessor (window=128, 5 OHLCV features, rolling
+z-score over 256 bars), direct_fixed_sltp, pnl_reward, synthetic EURUSD 1-min candles (2^19 bars).
+
+ours:       K steps as one CUDA-graph replay of K kernel launches (fxenv_step_many), actions pre-generated on the
+            device, observation rows rotating through a ring LARGER than L2 so every step's stores reach HBM.
+            `value` = whole-job env-steps/s (inputs resident in HBM), max-over-ranks device time.
+            `e2e`   = same metric through the reference-facing host-buffer call (fxenv_step_host): per step H2D of
+            the actions from pinned memory, the kernel, D2H of obs/reward/terminated, host sync.
+            `roofline` = algorithmic bytes per launch / average launch duration vs measured HBM peak.
+            `cpu_baseline` = the C oracle port timed on this box's host cores (rank 0, N=1, bounded sample).
+reference:  the CPU arm: the oracle port (oracle/fxenv_oracle.c; the Python reference cannot travel to the GPU box)
+            stepping the SAME workload with all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "golden")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+OHLCV = ["OPEN", "HIGH", "LOW", "CLOSE", "VOLUME"]
+DEFAULTS = {"initial_cash": 10000.0, "position_size": 1.0, "commission": 0.0, "slippage": 0.0, "price_column": "CLOSE"}
+WORKLOADS = {
+    # name: (envs/GPU, window, strategy, reward, pairs, R = reward-state bytes per env-step)
+    "cfg2": (4096, 128, "direct_fixed_sltp", "pnl_reward", 1, 0),
+    "cfg3": (16384, 256, "direct_atr_sltp", "dd_penalized_reward", 1, 16),
+    "cfg4": (4096, 128, "direct_fixed_sltp", "sharpe_reward", 1, 520),
+    "cfg5": (8192, 512, "direct_atr_sltp", "sharpe_reward", 4, 520),
+}
+T_BARS = 1 << 19
+L2_BYTES = 126 * 1024 * 1024
+
+
+def build_workload(name, envs_override=None):
+    import scenarios as S
+    from gym_fx_b200.config import lower_config
+    from gym_fx_b200.synth import PAIR_PIP, synth_candles, synth_minutes
+
+    envs, W, strat, rew, pairs, R = WORKLOADS[name]
+    if envs_override:
+        envs = envs_override
+    cfgd = {**DEFAULTS, "window_size": W, "feature_columns": list(OHLCV)}
+    pl = S.build_mirror_plugins(cfgd, {**S.DEFAULT_PLUGINS, "strategy": strat, "reward": rew,
+                                       "preprocessor": "feature_window_preprocessor"})
+    cfg = lower_config(cfgd, broker_plugin=pl["broker"], strategy_plugin=pl["strategy"],
+                       preprocessor_plugin=pl["preprocessor"], reward_plugin=pl["reward"], columns=OHLCV,
+                       num_envs=envs, num_pairs=pairs, order_capacity=256,
+                       pair_pip_size=list(PAIR_PIP[:pairs]) if pairs > 1 else None)
+    candles = [synth_candles(T_BARS, p) for p in range(pairs)]
+    minutes = [synth_minutes(T_BARS) for _ in range(pairs)]
+    D = W * 5 + 2 * W + 4
+    algo_bytes = 4 * D + 4 + 1 + 4 + R  # per env-step
+    desc = (f"{name}: {envs} envs/GPU, feature_window W={W} F=5 rolling_zscore S=256, {strat}, {rew}, "
+            f"{pairs} pair(s), synthetic 1-min candles T=2^19")
+    return cfg, candles, minutes, envs, D, algo_bytes, desc
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason sampler running during the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "50", "-i", str(index)], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_port_rate(workload, total_envs, steps, warmup, threads, budget_s=None):
+    """env-steps/s of the oracle port on the host.  Each step = one lockstep tick of `total_envs` envs."""
+    from gym_fx_b200.synth import start_offsets
+    from oracle.c_oracle import OracleVec, ParallelStepper
+    import ctypes as C
+
+    cfg, candles, minutes, envs, D, _, desc = build_workload(workload, total_envs)
+    vec = OracleVec(cfg, candles, minutes)
+    vec.reset(start_offsets(total_envs, T_BARS, steps + warmup, 256))
+    ps = ParallelStepper(vec, threads)
+    rng = np.random.default_rng(1234)
+    acts = rng.integers(0, 3, (64, total_envs)).astype(np.int32)
+    for k in range(warmup):
+        ps.step(acts[k % 64])
+    t0 = time.perf_counter()
+    done = 0
+    for k in range(steps):
+        ps.step(acts[k % 64])
+        done += 1
+        if budget_s is not None and time.perf_counter() - t0 > budget_s and done >= 5:
+            break
+    dt = time.perf_counter() - t0
+    vec.close()
+    return total_envs * done / dt, done, dt, ps.threads, desc
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU arm (oracle port, all host threads), rank 0 only."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    envs_per_gpu = args.envs or WORKLOADS[args.workload][0]
+    total = envs_per_gpu * args.gpus
+    rate, done, dt, used, desc = cpu_port_rate(args.workload, total, args.steps, args.warmup, threads)
+    line = {
+        "impl": "reference", "metric": "env-steps/sec", "value": rate, "unit": "env-steps/s", "n_gpus": args.gpus,
+        "steps": done, "warmup": args.warmup, "ms_per_step": dt / done * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "total_envs": total,
+                   "note": "CPU arm: C port of the reference path (oracle/fxenv_oracle.c); the Python reference "
+                           "(~1.3-1.5k steps/s/process per SURVEY section 6) cannot travel to the GPU box"},
+        "cpu_baseline": {"value": rate, "unit": "env-steps/s", "cores": used, "kind": "port",
+                         "sample": f"{total} envs x {done} lockstep steps, all {used} host threads (pthreads)"},
+        "e2e": {"value": rate, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    from gym_fx_b200.synth import start_offsets
+    from gym_fx_b200.vec_env import VecFxEnv
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device for --impl ours"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=dev)
+    cfg, candles, minutes, N, D, algo_bytes, desc = build_workload(args.workload, args.envs)
+    K, Wm = args.steps, max(3, args.warmup)
+    env = VecFxEnv(cfg, candles, minutes, device=dev)
+    # envs are sharded by rank: global env id = rank * N + i (no collective in the data path)
+    starts = torch.as_tensor(start_offsets(N * world, T_BARS, K + Wm + 64, 256)[rank * N:(rank + 1) * N])
+    env.reset(starts)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    chunk = min(K, 500)                      # graph length; K is covered by ceil(K/chunk) replays
+    while K % chunk:
+        chunk -= 1
+    acts = torch.randint(0, 3, (chunk, N), generator=gen, device=dev, dtype=torch.int32)
+    slots = max(2, -(-int(L2_BYTES * 1.8) // (N * D * 4)))  # ring > 1.8x L2 so stores cannot just sit in L2
+    ring = torch.empty((slots, N, D), dtype=torch.float32, device=dev)
+    rews = torch.empty((chunk, N), dtype=torch.float32, device=dev)
+    terms = torch.empty((chunk, N), dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    # warm-up (also instantiates the graph)
+    wchunks = -(-Wm // chunk)
+    for _ in range(max(1, wchunks)):
+        env.step_many(acts, ring, rews, terms)
+    torch.cuda.synchronize(dev)
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = env.launch_count()
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(K // chunk):
+        env.step_many(acts, ring, rews, terms)
+    ev1.record(stream)
+    torch.cuda.synchronize(dev)
+    if dist:
+        dist.barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = env.launch_count() - launches0
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    clocks = sampler.stop() if sampler else None
+    overflow = int((env.info()["flags"] & 16).ne(0).sum().item())
+    term_frac = float(terms.float().mean().item())
+
+    # ---- e2e: reference-facing host-buffer call, copies inside the timed region
+    Ke = min(K, 200)
+    h_act = torch.empty(N, dtype=torch.int32).pin_memory()
+    h_acts_all = acts[:min(chunk, Ke)].cpu()
+    h_obs = torch.empty((N, D), dtype=torch.float32).pin_memory()
+    h_rew = torch.empty(N, dtype=torch.float32).pin_memory()
+    h_term = torch.empty(N, dtype=torch.uint8).pin_memory()
+    for k in range(3):
+        h_act.copy_(h_acts_all[k % h_acts_all.shape[0]])
+        env.step_host(h_act, h_obs, h_rew, h_term)
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for k in range(Ke):
+        h_act.copy_(h_acts_all[k % h_acts_all.shape[0]])
+        env.step_host(h_act, h_obs, h_rew, h_term)   # synchronous: returns when the results are in host memory
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if dist:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_rate = N * world * Ke / float(te.item())
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        per_launch_s = ms_max * 1e-3 / K
+        achieved = N * algo_bytes / per_launch_s / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+                traffic = json.load(fh).get(args.workload)
+        except Exception:
+            pass
+        line = {
+            "metric": "env-steps/sec", "value": N * world * K / (ms_max * 1e-3), "unit": "env-steps/s",
+            "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms_max / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "envs_per_gpu": N, "obs_dim": D, "parallelism": f"env-shard x{world}",
+                       "actions": "uniform {0,1,2}, torch.Generator(seed=1234+rank), pre-generated on device",
+                       "l2": f"obs rows rotate through a {slots}-slot ring ({slots * N * D * 4 / 2**20:.0f} MiB > 126 MiB L2)",
+                       "graph": f"{chunk} step kernels per CUDA-graph replay", "order_overflow_envs": overflow,
+                       "terminated_frac": term_frac},
+            "clocks": clocks,
+            "e2e": {"value": e2e_rate, "unit": "env-steps/s", "h2d_bytes_per_step": N * 4,
+                    "d2h_bytes_per_step": N * (D * 4 + 4 + 1), "steps": Ke,
+                    "note": "fxenv_step_host: pinned host buffers, synchronous per step (PCIe-bound)"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "fx_step_kernel",
+                         "algorithmic_bytes_per_launch": N * algo_bytes,
+                         "avg_launch_us": per_launch_s * 1e6},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            sample_envs = min(N, 4096)
+            rate, done, dt, used, _ = cpu_port_rate(args.workload, sample_envs, 100000, 3, threads, budget_s=8.0)
+            line["cpu_baseline"] = {"value": rate, "unit": "env-steps/s", "cores": used, "kind": "port",
+                                    "sample": f"{sample_envs} envs x {done} lockstep steps ({dt:.1f} s), C oracle port, "
+                                              f"{used} host threads"}
+        print(json.dumps(line), flush=True)
+    env.close()
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--envs", type=int, default=None, help="envs per GPU (default: the workload's)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit(f"--gpus {args.gpus} needs torchrun (python -m torch.distributed.run --nproc-per-node {args.gpus} ...)")
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

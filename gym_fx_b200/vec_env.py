@@ -1,0 +1,195 @@
+"""
+VecFxEnv -- N lock-stepped gym-fx environments on one GPU, torch tensors in and out, no host round trip.
+
+Semantics per env are those of the reference's GymFxEnv.reset/step (app/env.py:102-172); every step of all N
+envs is ONE launch of the fused sm_100a kernel in libfxenv.so.  torch is used only for device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, Dict, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _native
+from .config import FxConfig, obs_dim, obs_layout
+
+
+class VecFxEnv:
+    """
+    cfg      FxConfig from gym_fx_b200.config.lower_config (num_envs, plugin selection and parameters)
+    candles  one float64 [T, n_cols] array per currency pair (env i trades pair i % num_pairs)
+    minutes  optional int64 [T] minutes-since-epoch per pair (ATR session filter)
+    """
+
+    def __init__(self, cfg: FxConfig, candles: Sequence[np.ndarray], minutes: Optional[Sequence[np.ndarray]] = None,
+                 device: Optional[torch.device | str | int] = None):
+        if not torch.cuda.is_available():
+            raise _native.FxEnvError("VecFxEnv needs a CUDA device (libfxenv.so has no CPU path)")
+        self.L = _native.load()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.type != "cuda":
+            raise _native.FxEnvError("VecFxEnv device must be a CUDA device")
+        self.cfg = cfg
+        self.num_envs = int(cfg.num_envs)
+        self.obs_dim = int(obs_dim(cfg))
+        self.layout = obs_layout(cfg)
+        if len(candles) != cfg.num_pairs:
+            raise ValueError(f"expected {cfg.num_pairs} candle tables, got {len(candles)}")
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            rc = self.L.fxenv_create(C.byref(cfg), C.byref(self._h))
+            _native.check(self.L, None, rc, "fxenv_create")
+            assert self.L.fxenv_obs_dim(self._h) == self.obs_dim
+            self.total_rows = []
+            for p, tab in enumerate(candles):
+                tab = np.ascontiguousarray(tab, dtype=np.float64)
+                if tab.ndim != 2 or tab.shape[1] != cfg.n_cols:
+                    raise ValueError(f"candle table {p} must be [T, {cfg.n_cols}]")
+                m = None if minutes is None or minutes[p] is None else np.ascontiguousarray(minutes[p], np.int64)
+                rc = self.L.fxenv_load_candles(self._h, p, tab.ctypes.data, tab.shape[0],
+                                               None if m is None else m.ctypes.data)
+                _native.check(self.L, self._h, rc, "fxenv_load_candles")
+                self.total_rows.append(tab.shape[0])
+        N, D, dev = self.num_envs, self.obs_dim, self.device
+        self.obs = torch.empty((N, D), dtype=torch.float32, device=dev)
+        self.reward = torch.empty(N, dtype=torch.float32, device=dev)
+        self.reward64 = torch.empty(N, dtype=torch.float64, device=dev)
+        self.terminated = torch.empty(N, dtype=torch.uint8, device=dev)
+        self.truncated = torch.zeros(N, dtype=torch.bool, device=dev)  # always False (app/env.py:158)
+        self._info_ptrs = _native.FxInfoPtrs()
+        self.L.fxenv_get_info(self._h, C.byref(self._info_ptrs))
+        self._info_views: Dict[str, torch.Tensor] = {}
+        self.action_dtype = torch.float32 if cfg.action_mode == 1 else torch.int32
+
+    # ------------------------------------------------------------------ lifecycle
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self.L.fxenv_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    # ------------------------------------------------------------------ Gym-style API
+    def reset(self, start_bars: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None):
+        """-> (obs [N, D] float32, info).  start_bars: int64 [N] first table row of each env's episode window."""
+        sb = mk = None
+        if start_bars is not None:
+            sb = torch.as_tensor(start_bars, dtype=torch.int64, device=self.device).contiguous()
+        if mask is not None:
+            mk = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+        rc = self.L.fxenv_reset(self._h, None if sb is None else sb.data_ptr(), None if mk is None else mk.data_ptr(),
+                                self._stream())
+        _native.check(self.L, self._h, rc, "fxenv_reset")
+        rc = self.L.fxenv_observe(self._h, self.obs.data_ptr(), self._stream())
+        _native.check(self.L, self._h, rc, "fxenv_observe")
+        return self.obs, self.info()
+
+    def step(self, actions: torch.Tensor, out_obs: Optional[torch.Tensor] = None):
+        """-> (obs, reward float32 [N], terminated bool [N], truncated bool [N], info).
+        The returned tensors are views of buffers that the next step() overwrites."""
+        a = actions
+        if a.dtype != self.action_dtype or a.device != self.device or not a.is_contiguous():
+            a = a.to(device=self.device, dtype=self.action_dtype).contiguous()
+        a = a.reshape(-1)
+        if a.numel() != self.num_envs:
+            raise ValueError(f"expected {self.num_envs} actions")
+        obs = self.obs if out_obs is None else out_obs
+        rc = self.L.fxenv_step(self._h, a.data_ptr(), obs.data_ptr(), self.reward.data_ptr(),
+                               self.terminated.data_ptr(), self.reward64.data_ptr(), self._stream())
+        _native.check(self.L, self._h, rc, "fxenv_step")
+        return obs, self.reward, self.terminated.view(torch.bool), self.truncated, self.info()
+
+    def step_many(self, actions: torch.Tensor, obs_ring: torch.Tensor, rewards: torch.Tensor, terminated: torch.Tensor):
+        """K consecutive steps as one cached CUDA graph.  actions [K, N]; obs_ring [slots, N, D];
+        rewards float32 [K, N]; terminated uint8 [K, N]."""
+        K = actions.shape[0]
+        rc = self.L.fxenv_step_many(self._h, int(K), actions.data_ptr(), obs_ring.data_ptr(), int(obs_ring.shape[0]),
+                                    rewards.data_ptr(), terminated.data_ptr(), self._stream())
+        _native.check(self.L, self._h, rc, "fxenv_step_many")
+
+    def step_host(self, actions_host: torch.Tensor, obs_host: torch.Tensor, reward_host: torch.Tensor,
+                  terminated_host: torch.Tensor):
+        """Reference-facing call with (pinned) HOST tensors: H2D actions, one step, D2H results, synchronous."""
+        rc = self.L.fxenv_step_host(self._h, actions_host.data_ptr(), obs_host.data_ptr(), reward_host.data_ptr(),
+                                    terminated_host.data_ptr())
+        _native.check(self.L, self._h, rc, "fxenv_step_host")
+
+    # ------------------------------------------------------------------ info / state
+    def _view(self, name: str) -> torch.Tensor:
+        v = self._info_views.get(name)
+        if v is None:
+            ptr = getattr(self._info_ptrs, name)
+            dt = getattr(torch, _native.INFO_DTYPES[name])
+            v = _tensor_from_ptr(ptr, self.num_envs, dt, self.device)
+            self._info_views[name] = v
+        return v
+
+    def info(self) -> Dict[str, torch.Tensor]:
+        """Zero-copy views of the device-side info columns (app/env.py:244-254,162-166)."""
+        return _LazyInfo(self)
+
+    def obs_dict(self, obs: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        """Split flat rows into the reference's Dict observation (views)."""
+        o = self.obs if obs is None else obs
+        return {k: o[:, off:off + int(np.prod(shape))].reshape((o.shape[0],) + tuple(shape))
+                for k, (off, shape) in self.layout.items()}
+
+    def launch_count(self) -> int:
+        return int(self.L.fxenv_launch_count(self._h))
+
+    def get_state(self) -> bytes:
+        n = self.L.fxenv_state_bytes(self._h)
+        buf = (C.c_char * n)()
+        _native.check(self.L, self._h, self.L.fxenv_get_state(self._h, buf, n), "fxenv_get_state")
+        return bytes(buf)
+
+    def set_state(self, blob: bytes):
+        _native.check(self.L, self._h, self.L.fxenv_set_state(self._h, blob, len(blob)), "fxenv_set_state")
+
+
+class _LazyInfo(dict):
+    """dict of info tensors materialised on first access (keeps step() free of Python overhead)."""
+
+    KEYS = tuple(_native.INFO_DTYPES)
+
+    def __init__(self, env: VecFxEnv):
+        super().__init__()
+        self._env = env
+
+    def __missing__(self, key):
+        if key == "pnl":
+            v = self._env._view("equity") - self._env._view("prev_equity")
+        elif key == "reward":
+            v = self._env.reward
+        elif key in self.KEYS:
+            v = self._env._view(key)
+        else:
+            raise KeyError(key)
+        self[key] = v
+        return v
+
+    def keys(self):
+        return list(self.KEYS) + ["pnl", "reward"]
+
+    def __contains__(self, key):
+        return key in self.KEYS or key in ("pnl", "reward")
+
+
+class _CudaArrayView:
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (int(ptr), False), "version": 3}
+
+
+def _tensor_from_ptr(ptr: int, n: int, dtype: torch.dtype, device: torch.device) -> torch.Tensor:
+    typestr = {torch.float64: "<f8", torch.int32: "<i4", torch.int64: "<i8", torch.uint8: "|u1"}[dtype]
+    with torch.cuda.device(device):
+        return torch.as_tensor(_CudaArrayView(ptr, n, typestr), device=device)

@@ -57,6 +57,7 @@ def lib():
         L.fxo_obs_dim.argtypes = [C.POINTER(FxConfig)]
         L.fxo_step_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                      C.c_void_p, C.c_void_p, C.c_void_p]
+        L.fxo_step_batch_mt.argtypes = L.fxo_step_batch.argtypes + [C.c_int]
         assert L.fxo_config_size() == C.sizeof(FxConfig), "FxConfig layout mismatch (python vs C)"
         assert L.fxo_info_size() == C.sizeof(FxoInfo)
         _lib = L
@@ -143,3 +144,26 @@ class OracleVec:
 
     def max_live_orders(self):
         return max(self.L.fxo_max_live_orders(h) for h in self.envs)
+
+
+class ParallelStepper:
+    """Steps an OracleVec with `threads` host threads (pthreads inside fxo_step_batch_mt, contiguous env slices).
+    Used by bench.py's cpu_baseline / --impl reference legs only."""
+
+    def __init__(self, vec: OracleVec, threads: int):
+        self.vec = vec
+        self.threads = max(1, min(int(threads), vec.N, 1024))
+        self.obs = np.empty((vec.N, vec.D), np.float32)
+        self.rew = np.empty(vec.N, np.float32)
+        self.term = np.empty(vec.N, np.uint8)
+
+    def step(self, actions: np.ndarray):
+        v = self.vec
+        is_f = v.cfg.action_mode == 1
+        v.L.fxo_step_batch_mt(v._arr, v.N, None if is_f else actions.ctypes.data, actions.ctypes.data if is_f else None,
+                              self.obs.ctypes.data, v.D, self.rew.ctypes.data, None, self.term.ctypes.data,
+                              self.threads)
+        return self.obs, self.rew, self.term
+
+    def close(self):
+        pass

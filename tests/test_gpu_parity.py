@@ -1,0 +1,260 @@
+"""GPU (-m gpu) parity tests: the CUDA env (through the C-ABI, libfxenv.so) against
+  (1) the committed golden trajectories of the reference (tests/golden/*.npz), and
+  (2) the C oracle on the same seeded inputs, many envs in lockstep,
+plus full-size (BASELINE cfg2: 4096 envs, W=128, F=5) size-independent properties.
+
+Bars: integer/index state and fp64 account state bit-exact; rewards 1e-5 relative in fp32 (north_star) and 1e-9
+in fp64; observations rtol 1e-5 / atol 2e-6 in fp32 (the z-score uses a reciprocal multiply and a warp-ordered
+sum, the oracle divides and sums sequentially)."""
+import numpy as np
+import pytest
+import torch
+
+import scenarios as S
+from common import assert_traj_matches, config_from_meta, golden_names, load_golden, replay
+from common_gpu import GpuVec, compare_info, compare_step
+from gym_fx_b200.config import lower_config
+from gym_fx_b200.synth import start_offsets, synth_candles, synth_minutes
+from oracle.c_oracle import OracleVec
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_cuda():
+    assert torch.cuda.is_available(), "GPU tests selected but no CUDA device is visible"
+
+
+# ---------------------------------------------------------------------------------------------- (1) goldens
+@pytest.mark.parametrize("name", golden_names())
+def test_gpu_matches_reference_golden(name):
+    g = load_golden(name)
+    cfg = config_from_meta(g["meta"], order_capacity=512)
+    env = GpuVec(cfg, [g["candles"]], [g["minutes"]])
+    traj = replay(env, g, env.info)
+    assert not np.any(env.info()["flags"] & 16), "order table overflow"
+    env.close()
+    assert_traj_matches(traj, g, obs_rtol=1e-5, obs_atol=2e-6, label=name)
+
+
+def test_gpu_reference_known_answer():
+    # examples/results/buy_hold_summary.json:3-4 of the reference, produced through REAL backtrader
+    g = load_golden("buy_hold_uptrend")
+    env = GpuVec(config_from_meta(g["meta"]), [g["candles"]], [g["minutes"]])
+    traj = replay(env, g, env.info)
+    assert traj["equity"][-1] == 10000.095791583166
+
+
+# ---------------------------------------------------------------------------------------------- (2) vs oracle
+def _mk(cfgd, plugins, N, T=4096, pairs=1, columns=None, **kw):
+    cfgd = {**S.DEFAULTS, **cfgd}
+    pl = S.build_mirror_plugins(cfgd, {**S.DEFAULT_PLUGINS, **plugins})
+    cfg = lower_config(cfgd, broker_plugin=pl["broker"], strategy_plugin=pl["strategy"],
+                       preprocessor_plugin=pl["preprocessor"], reward_plugin=pl["reward"],
+                       columns=columns or S.OHLCV, num_envs=N, num_pairs=pairs, **kw)
+    candles = [synth_candles(T, p) for p in range(pairs)]
+    minutes = [synth_minutes(T) for _ in range(pairs)]
+    return cfg, candles, minutes
+
+
+FW = {"feature_columns": list(S.OHLCV)}
+VEC_CASES = {
+    # BASELINE configs[1] shape: feature_window W=128 F=5 S=256, direct_fixed_sltp, pnl
+    "cfg2_fixed_fw128_pnl": (dict(window_size=128, **FW), dict(strategy="direct_fixed_sltp",
+                             preprocessor="feature_window_preprocessor"), {}),
+    # configs[2] shape: W=256, direct_atr_sltp, dd_penalized
+    "cfg3_atr_fw256_dd": (dict(window_size=256, **FW), dict(strategy="direct_atr_sltp",
+                          preprocessor="feature_window_preprocessor", reward="dd_penalized_reward"), {}),
+    # configs[3] shape: W=128 + sharpe
+    "cfg4_fixed_fw128_sharpe": (dict(window_size=128, **FW), dict(strategy="direct_fixed_sltp",
+                                preprocessor="feature_window_preprocessor", reward="sharpe_reward"), {}),
+    # configs[4] shape (scaled down): 4 pairs interleaved, W=512, atr, sharpe
+    "cfg5_atr_fw512_sharpe_4pairs": (dict(window_size=512, **FW), dict(strategy="direct_atr_sltp",
+                                     preprocessor="feature_window_preprocessor", reward="sharpe_reward"),
+                                     dict(pairs=4, pair_pip_size=[1e-4, 1e-4, 1e-4, 1e-2])),
+    "cfg1_default": (dict(window_size=32), {}, {}),
+    "commission_leverage_relvol": (dict(window_size=16, commission=2e-5, leverage=5.0, rel_volume=0.3,
+                                        max_order_volume=9000.0), dict(strategy="direct_atr_sltp"), {}),
+    "margin_heavy_fixed": (dict(window_size=8, position_size=6000.0, commission=5e-5, sl_pips=4.0, tp_pips=6.0),
+                           dict(strategy="direct_fixed_sltp", reward="dd_penalized_reward"), {}),
+}
+
+
+@pytest.mark.parametrize("case", sorted(VEC_CASES))
+def test_gpu_matches_oracle_vectorised(case):
+    cfgd, plugins, kw = VEC_CASES[case]
+    N, T, steps = 192, 6000, 330
+    cfg, candles, minutes = _mk(cfgd, plugins, N, T=T, order_capacity=512, **kw)
+    starts = start_offsets(N, T, steps + 10, 300)
+    starts[:8] = [0, 1, 2, 5, 100, 255, 256, 257]  # warm-up edge offsets
+    gpu, orc = GpuVec(cfg, candles, minutes), OracleVec(cfg, candles, minutes)
+    np.testing.assert_allclose(gpu.reset(starts), orc.reset(starts), rtol=1e-5, atol=2e-6, err_msg="reset obs")
+    rng = np.random.default_rng(2024)
+    inexact = 0
+    for k in range(steps):
+        a = rng.integers(0, 3, N).astype(np.int32)
+        inexact += compare_step(f"{case} step {k}", gpu.step(a), orc.step(a))
+        if k % 25 == 0 or k == steps - 1:
+            compare_info(f"{case} step {k}", gpu.info(), orc.info())
+    assert not np.any(gpu.info()["flags"] & 16), "order table overflow"
+    total = steps * N * gpu.env.obs_dim
+    assert inexact <= max(10, total * 1e-4), f"{inexact}/{total} obs floats not bit-identical to the oracle"
+    gpu.close()
+
+
+def test_gpu_episode_end_and_auto_reset():
+    # data exhaustion (A.7), stepping after termination, next-step auto reset, masked reset
+    for auto in (False, True):
+        cfg, candles, minutes = _mk(dict(window_size=8, sl_pips=3.0, tp_pips=4.0), dict(strategy="direct_fixed_sltp",
+                                    reward="sharpe_reward"), 64, T=600, episode_bars=40, auto_reset=auto)
+        starts = (np.arange(64) * 7) % 500
+        gpu, orc = GpuVec(cfg, candles, minutes), OracleVec(cfg, candles, minutes)
+        gpu.reset(starts); orc.reset(starts)
+        rng = np.random.default_rng(5)
+        for k in range(95):
+            a = rng.integers(0, 3, 64).astype(np.int32)
+            compare_step(f"auto={auto} step {k}", gpu.step(a), orc.step(a))
+            compare_info(f"auto={auto} step {k}", gpu.info(), orc.info())
+            if k == 50:
+                mask = (np.arange(64) % 3 == 0).astype(np.uint8)
+                np.testing.assert_allclose(gpu.reset(None, mask), orc.reset(None, mask), rtol=1e-5, atol=2e-6)
+        gpu.close()
+
+
+def test_gpu_continuous_actions_and_bad_discrete():
+    cfg, candles, minutes = _mk(dict(window_size=8, action_space_mode="continuous"), dict(strategy="direct_fixed_sltp"), 32)
+    gpu, orc = GpuVec(cfg, candles, minutes), OracleVec(cfg, candles, minutes)
+    gpu.reset(np.zeros(32, np.int64)); orc.reset(np.zeros(32, np.int64))
+    rng = np.random.default_rng(1)
+    for k in range(120):
+        a = rng.uniform(-1, 1, 32).astype(np.float32)
+        a[k % 32] = 0.33 if k % 2 else -0.33  # exactly on the threshold
+        compare_step(f"cont {k}", gpu.step(a), orc.step(a))
+    gpu.close()
+    cfg, candles, minutes = _mk(dict(window_size=8), {}, 32)
+    gpu, orc = GpuVec(cfg, candles, minutes), OracleVec(cfg, candles, minutes)
+    gpu.reset(np.zeros(32, np.int64)); orc.reset(np.zeros(32, np.int64))
+    for k in range(60):
+        a = rng.integers(-3, 6, 32).astype(np.int32)  # out-of-range ints are coerced to hold (app/env.py:200-204)
+        compare_step(f"bad {k}", gpu.step(a), orc.step(a))
+    gpu.close()
+
+
+def test_gpu_order_overflow_flag_is_loud():
+    cfg, candles, minutes = _mk(dict(window_size=8), dict(strategy="direct_fixed_sltp"), 32, order_capacity=32)
+    gpu = GpuVec(cfg, candles, minutes)
+    gpu.reset(np.zeros(32, np.int64))
+    rng = np.random.default_rng(3)
+    for k in range(400):
+        gpu.step(rng.integers(0, 3, 32).astype(np.int32), want_obs=False)
+    inf = gpu.info()
+    assert np.any(inf["flags"] & 16), "a 32-entry table must overflow under random actions (reference is unbounded)"
+    assert inf["n_orders"].max() <= 32
+    gpu.close()
+
+
+# ---------------------------------------------------------------------------------------------- (3) full size
+@pytest.fixture(scope="module")
+def cfg2_full():
+    N, T = 4096, 1 << 17
+    cfg, candles, minutes = _mk(dict(window_size=128, **FW), dict(strategy="direct_fixed_sltp",
+                                preprocessor="feature_window_preprocessor"), N, T=T)
+    return N, T, cfg, candles, minutes
+
+
+def test_full_size_flat_policy_keeps_equity(cfg2_full):
+    # tools/smoke_test.py:113-118 of the reference: the flat driver leaves equity unchanged
+    N, T, cfg, candles, minutes = cfg2_full
+    gpu = GpuVec(cfg, candles, minutes)
+    gpu.reset(start_offsets(N, T, 300, 256))
+    z = np.zeros(N, np.int32)
+    for k in range(40):
+        obs, rew, rew64, term = gpu.step(z, want_obs=(k == 39))
+        assert np.all(rew64 == 0.0) and not term.any()
+    inf = gpu.info()
+    assert np.all(inf["equity"] == 10000.0) and np.all(inf["trades"] == 0) and np.all(inf["bar_index"] == 40)
+    assert np.all(np.isfinite(obs)) and np.all(np.abs(obs[:, :640]) <= 10.0)
+    gpu.close()
+
+
+def test_full_size_shard_invariance_determinism_and_sampled_oracle(cfg2_full):
+    # env i's trajectory must not depend on how many envs share the launch (what multi-GPU sharding relies on),
+    # must be reproducible, and a sample of envs must match the oracle at the full 4096-env size.
+    N, T, cfg, candles, minutes = cfg2_full
+    steps = 120
+    starts = start_offsets(N, T, steps, 256)
+    acts = np.random.default_rng(1234).integers(0, 3, (steps, N)).astype(np.int32)
+
+    def run(sel):
+        c2, _, _ = _mk(dict(window_size=128, **FW), dict(strategy="direct_fixed_sltp",
+                       preprocessor="feature_window_preprocessor"), len(sel), T=T)
+        g = GpuVec(c2, candles, minutes)
+        g.reset(starts[sel])
+        outs = [g.step(acts[k, sel], want_obs=(k % 40 == 39 or k == steps - 1)) for k in range(steps)]
+        inf = g.info()
+        g.close()
+        return outs, inf
+
+    full, finf = run(np.arange(N))
+    again, ainf = run(np.arange(N))
+    sel = np.arange(0, N, 8)
+    shard, sinf = run(sel)
+    for k in range(steps):
+        for j in range(4):
+            if full[k][j] is None:
+                continue
+            assert np.array_equal(full[k][j], again[k][j]), f"non-deterministic output {j} at step {k}"
+            assert np.array_equal(full[k][j][sel], shard[k][j]), f"shard-dependent output {j} at step {k}"
+    for key in ("equity", "cash", "trades", "n_orders"):
+        assert np.array_equal(finf[key][sel], sinf[key])
+    samp = np.arange(0, N, 64)
+    c3, _, _ = _mk(dict(window_size=128, **FW), dict(strategy="direct_fixed_sltp",
+                   preprocessor="feature_window_preprocessor"), len(samp), T=T)
+    orc = OracleVec(c3, candles, minutes)
+    orc.reset(starts[samp])
+    for k in range(steps):
+        oo = orc.step(acts[k, samp])
+        go = tuple(None if x is None else x[samp] for x in full[k])
+        compare_step(f"full-size sample step {k}", (go[0], go[1], go[2], go[3]), oo if go[0] is not None else (None,) + oo[1:])
+    oi = orc.info()
+    assert np.array_equal(finf["equity"][samp], oi["equity"]) and np.array_equal(finf["trades"][samp], oi["trades"])
+
+
+def test_step_many_graph_and_step_host_match_step(cfg2_full):
+    N, T, cfg, candles, minutes = cfg2_full
+    K = 24
+    starts = torch.as_tensor(start_offsets(N, T, 300, 256))
+    acts = torch.randint(0, 3, (K, N), dtype=torch.int32, generator=torch.Generator().manual_seed(7)).cuda()
+    from gym_fx_b200.vec_env import VecFxEnv
+    a_env, b_env, c_env = (VecFxEnv(cfg, candles, minutes) for _ in range(3))
+    for e in (a_env, b_env, c_env):
+        e.reset(starts)
+    D = a_env.obs_dim
+    ring = torch.empty((2, N, D), dtype=torch.float32, device="cuda")
+    rews = torch.empty((K, N), dtype=torch.float32, device="cuda")
+    terms = torch.empty((K, N), dtype=torch.uint8, device="cuda")
+    for rep in range(2):  # second call replays the cached graph
+        b_env.reset(starts)
+        b_env.step_many(acts, ring, rews, terms)
+    torch.cuda.synchronize()
+    h_act = torch.empty(N, dtype=torch.int32).pin_memory()
+    h_obs = torch.empty((N, D), dtype=torch.float32).pin_memory()
+    h_rew = torch.empty(N, dtype=torch.float32).pin_memory()
+    h_term = torch.empty(N, dtype=torch.uint8).pin_memory()
+    for k in range(K):
+        obs, rew, term, _, _ = a_env.step(acts[k])
+        h_act.copy_(acts[k])
+        c_env.step_host(h_act, h_obs, h_rew, h_term)
+        assert torch.equal(rew, rews[k]) and torch.equal(term.to(torch.uint8), terms[k])
+        assert torch.equal(rew.cpu(), h_rew) and torch.equal(obs.cpu(), h_obs)
+    assert torch.equal(obs, ring[(K - 1) % 2])
+    assert torch.equal(a_env.info()["equity"], b_env.info()["equity"])
+    # snapshot / restore round trip
+    blob = a_env.get_state()
+    ref = [a_env.step(acts[k])[1].clone() for k in range(3)]
+    a_env.set_state(blob)
+    for k in range(3):
+        assert torch.equal(a_env.step(acts[k])[1], ref[k])
+    assert a_env.launch_count() >= K
+    for e in (a_env, b_env, c_env):
+        e.close()
