@@ -153,6 +153,8 @@ int fxenv_create(const FxConfig* cfg, FxEnv** out) {
   env->P.cap = cap;
   env->P.obs_dim = (int32_t)fx_obs_dim(c);
   env->P.smem_per_warp = (int32_t)fx_smem_per_warp(c, cap);
+  ce = fx_configure_kernels((size_t)env->P.smem_per_warp * FX_WARPS_PER_BLOCK);
+  if (ce != cudaSuccess) { delete env; return cuda_fail(nullptr, ce, "order_capacity too large for shared memory"); }
   env->P.fast_features = 0;
   if (c.preproc == FX_PREPROC_FEATURE_WINDOW && c.n_features == c.n_cols) {
     env->P.fast_features = 1;

@@ -451,6 +451,14 @@ size_t fx_smem_per_warp(const FxConfig& cfg, int cap) {
   return (b + 15) & ~(size_t)15;
 }
 
+// dynamic shared memory above the 48 KB default needs an explicit opt-in per kernel
+cudaError_t fx_configure_kernels(size_t smem_per_block) {
+  if (smem_per_block <= 48 * 1024) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(fx_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_per_block);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(fx_observe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_per_block);
+}
+
 cudaError_t fx_launch_step(const FxKernelParams& P, const void* actions, float* obs, float* reward, double* reward64,
                            uint8_t* terminated, cudaStream_t stream) {
   const int N = P.cfg.num_envs;

@@ -50,3 +50,4 @@ cudaError_t fx_launch_reset(const FxKernelParams& P, const int64_t* start_bar, c
 cudaError_t fx_launch_observe(const FxKernelParams& P, float* obs, cudaStream_t stream);
 cudaError_t fx_launch_stats(const FxConfig& cfg, const double* candles, double* stats, int64_t T, cudaStream_t stream);
 size_t fx_smem_per_warp(const FxConfig& cfg, int cap);
+cudaError_t fx_configure_kernels(size_t smem_per_block);
