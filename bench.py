@@ -47,6 +47,7 @@ WORKLOADS = {
 }
 T_BARS = 1 << 19
 L2_BYTES = 126 * 1024 * 1024
+ORDER_CAP = int(os.environ.get("FXENV_ORDER_CAP", "128"))  # order-table entries per env (overflowing envs are reported)
 
 
 def build_workload(name, envs_override=None):
@@ -62,7 +63,7 @@ def build_workload(name, envs_override=None):
                                        "preprocessor": "feature_window_preprocessor"})
     cfg = lower_config(cfgd, broker_plugin=pl["broker"], strategy_plugin=pl["strategy"],
                        preprocessor_plugin=pl["preprocessor"], reward_plugin=pl["reward"], columns=OHLCV,
-                       num_envs=envs, num_pairs=pairs, order_capacity=256,
+                       num_envs=envs, num_pairs=pairs, order_capacity=ORDER_CAP,
                        pair_pip_size=list(PAIR_PIP[:pairs]) if pairs > 1 else None)
     candles = [synth_candles(T_BARS, p) for p in range(pairs)]
     minutes = [synth_minutes(T_BARS) for _ in range(pairs)]

@@ -2,6 +2,7 @@
 // No torch types, no exceptions across the boundary; every entry point returns a status code.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -152,43 +153,53 @@ int fxenv_create(const FxConfig* cfg, FxEnv** out) {
   c.order_capacity = cap;
   env->P.cap = cap;
   env->P.obs_dim = (int32_t)fx_obs_dim(c);
-  env->P.smem_per_warp = (int32_t)fx_smem_per_warp(c, cap);
-  ce = fx_configure_kernels((size_t)env->P.smem_per_warp * FX_WARPS_PER_BLOCK);
-  if (ce != cudaSuccess) { delete env; return cuda_fail(nullptr, ce, "order_capacity too large for shared memory"); }
-  env->P.fast_features = 0;
-  if (c.preproc == FX_PREPROC_FEATURE_WINDOW && c.n_features == c.n_cols) {
-    env->P.fast_features = 1;
-    for (int i = 0; i < c.n_features; i++) if (c.feature_cols[i] != i) env->P.fast_features = 0;
+  env->P.inv_initial_cash = 1.0 / (c.initial_cash != 0.0 ? c.initial_cash : 1.0);
+  if (const char* dv = getenv("FXENV_DEBUG")) env->P.debug = atoi(dv);  // timing experiments only
+  if (const char* tv = getenv("FXENV_TIMING")) {
+    if (atoi(tv)) {
+      cudaMalloc(&env->P.timing, (size_t)c.num_envs * FX_NSTAMP * sizeof(long long));
+      cudaMemset(env->P.timing, 0, (size_t)c.num_envs * FX_NSTAMP * sizeof(long long));
+    }
   }
+  env->P.fast_features = 0;
+  if (c.preproc == FX_PREPROC_FEATURE_WINDOW && c.n_features == 5 && c.n_cols == 5) {
+    env->P.fast_features = 5;
+    for (int i = 0; i < 5; i++) if (c.feature_cols[i] != i) env->P.fast_features = 0;
+  }
+  ce = fx_configure_kernels(env->P);
+  if (ce != cudaSuccess) { delete env; return cuda_fail(nullptr, ce, "order_capacity too large for shared memory"); }
   // one slab for the whole per-env state (snapshot == one memcpy)
   const size_t N = (size_t)c.num_envs;
   const size_t ring = (c.reward == FX_REWARD_SHARPE) ? (size_t)c.sharpe_window : 1;
   SlabPlan plan;
-  size_t o_d[9], o_start, o_i[10], o_flags, o_ring, o_meta, o_p0, o_p1, o_sz;
-  for (int i = 0; i < 9; i++) o_d[i] = plan.add(N * 8);
+  const size_t capP = (size_t)cap + FXO_SLACK;
+  size_t o_d[8], o_start, o_i[10], o_flags, o_ring, o_welford, o_meta, o_p0, o_p1, o_sz;
+  for (int i = 0; i < 8; i++) o_d[i] = plan.add(N * 8);
   o_start = plan.add(N * 8);
   for (int i = 0; i < 10; i++) o_i[i] = plan.add(N * 4);
   o_flags = plan.add(N * 4);
   o_ring = plan.add(N * ring * 8);
-  o_meta = plan.add(N * cap * 4);
-  o_p0 = plan.add(N * cap * 8);
-  o_p1 = plan.add(N * cap * 8);
-  o_sz = plan.add(N * cap * 8);
+  o_welford = plan.add(N * FXENV_MAX_FEATURES * 2 * 8);
+  o_meta = plan.add(N * capP * 4);
+  o_p0 = plan.add(N * capP * 8);
+  o_p1 = plan.add(N * capP * 8);
+  o_sz = plan.add(N * capP * 8);
   env->slab_bytes = plan.bytes;
   ce = cudaMalloc(&env->slab, plan.bytes);
   if (ce != cudaSuccess) { delete env; return cuda_fail(nullptr, ce, "cudaMalloc(state slab)"); }
   cudaMemset(env->slab, 0, plan.bytes);
   FxDeviceState& st = env->P.st;
   unsigned char* b = env->slab;
-  double** dcols[9] = {&st.cash, &st.psize, &st.pprice, &st.value, &st.equity, &st.prev_equity, &st.price,
+  double** dcols[8] = {&st.cash, &st.psize, &st.pprice, &st.equity, &st.prev_equity, &st.price,
                        &st.commission_paid, &st.dd_peak};
-  for (int i = 0; i < 9; i++) *dcols[i] = reinterpret_cast<double*>(b + o_d[i]);
+  for (int i = 0; i < 8; i++) *dcols[i] = reinterpret_cast<double*>(b + o_d[i]);
   st.start = reinterpret_cast<int64_t*>(b + o_start);
   int32_t** icols[10] = {&st.t, &st.total_bars, &st.position, &st.bar_index, &st.trades, &st.n_orders,
                          &st.sh_len, &st.sh_head, &st.sh_last_step, &st.dd_last_step};
   for (int i = 0; i < 10; i++) *icols[i] = reinterpret_cast<int32_t*>(b + o_i[i]);
   st.flags = reinterpret_cast<uint32_t*>(b + o_flags);
   st.sh_ring = reinterpret_cast<double*>(b + o_ring);
+  st.welford = reinterpret_cast<double*>(b + o_welford);
   st.o_meta = reinterpret_cast<uint32_t*>(b + o_meta);
   st.o_p0 = reinterpret_cast<double*>(b + o_p0);
   st.o_p1 = reinterpret_cast<double*>(b + o_p1);
@@ -205,6 +216,7 @@ int fxenv_destroy(FxEnv* env) {
     cudaFree(env->candles_dev[p]); cudaFree(env->stats_dev[p]); cudaFree(env->minutes_dev[p]);
   }
   cudaFree(env->slab);
+  cudaFree(env->P.timing);
   cudaFree(env->h_actions); cudaFree(env->h_obs); cudaFree(env->h_reward); cudaFree(env->h_term);
   if (env->hstream) cudaStreamDestroy(env->hstream);
   delete env;
@@ -384,5 +396,15 @@ int fxenv_set_state(FxEnv* env, const void* buf_host, int64_t nbytes) {
 }
 
 int64_t fxenv_launch_count(const FxEnv* env) { return env ? env->launches : -1; }
+
+/* debug (FXENV_TIMING=1): copies the [num_envs][10] clock64() phase stamps of the last step; returns 10 or <0 */
+int fxenv_debug_timings(FxEnv* env, long long* out_host) {
+  if (!env || !out_host || !env->P.timing) return FXENV_E_STATE;
+  DeviceGuard g(env->device);
+  cudaDeviceSynchronize();
+  if (cudaMemcpy(out_host, env->P.timing, (size_t)env->P.cfg.num_envs * FX_NSTAMP * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess)
+    return FXENV_E_CUDA;
+  return FX_NSTAMP;
+}
 
 }  // extern "C"

@@ -34,8 +34,10 @@
 
 #if defined(__CUDACC__)
 #define FX_HD __host__ __device__ __forceinline__
+#define FX_HD_COLD static __host__ __device__ __noinline__  // rare paths: keep them out of the hot instruction stream
 #else
 #define FX_HD inline
+#define FX_HD_COLD inline
 #endif
 
 // ---- order-table entry encoding ---------------------------------------------------------------------------------
@@ -47,6 +49,7 @@
 #define FXO_ACTIVE 8u         // PAIR: parent has completed and the children may trigger
 #define FXO_ACTIVATE_NEXT 16u // PAIR: queued in broker._toactivate (activated at the start of the next bar)
 #define FXO_DEAD 32u          // executed / cancelled / rejected: dropped by the next compaction
+#define FXO_SELL 64u          // the entry's signed size is negative (lets the trigger scan skip loading the size)
 
 struct FxBar {
   double o, h, l, c;
@@ -65,10 +68,22 @@ struct FxOrderTab {
   double* p0;
   double* p1;
   double* sz;
-  int n;    // live entries
-  int cap;  // capacity
+  int n;           // entries in the table (live + not-yet-compacted dead ones)
+  int cap;         // logical capacity (live entries); the arrays hold cap + FXO_SLACK
   int dirty_from;  // smallest index whose stored copy is stale (n => nothing to write back)
+  int ndead;       // entries marked FXO_DEAD since the last compaction
 };
+
+#define FXO_SLACK 32  // physical head-room: new orders are appended before the dead ones are compacted away
+
+FX_HD void fx_kill(FxOrderTab& t, int k) {
+  const uint32_t m = t.meta[k];
+  if (!(m & FXO_DEAD)) {
+    t.meta[k] = m | FXO_DEAD;
+    t.ndead++;
+    if (k < t.dirty_from) t.dirty_from = k;
+  }
+}
 
 // ---- Position.update (backtrader position.py) ------------------------------------------------------------------
 FX_HD void fx_pos_update(double& psize, double& pprice, double size, double price, double& opened, double& closed) {
@@ -96,14 +111,14 @@ FX_HD void fx_pseudo_execute(const FxConfig& c, double size, double price, doubl
   if (closed != 0.0) {
     const double closedvalue = (-closed) * price;  // pprice_orig == created.price in pseudo mode
     double closecash = closedvalue;
-    if (closedvalue > 0.0) closecash /= c.leverage;
+    if (closedvalue > 0.0 && c.leverage != 1.0) closecash /= c.leverage;
     cash += closecash + 0.0;                       // pnl = 0 in pseudo mode
     cash -= fabs(closed) * c.commission * price;
   }
   if (opened != 0.0) {
     const double openedvalue = opened * price;
     double opencash = openedvalue;
-    if (openedvalue > 0.0) opencash /= c.leverage;
+    if (openedvalue > 0.0 && c.leverage != 1.0) opencash /= c.leverage;
     cash -= opencash;
     cash -= fabs(opened) * c.commission * price;
   }
@@ -120,7 +135,7 @@ FX_HD bool fx_execute(const FxConfig& c, FxEnvRegs& e, double size, double price
   if (closed != 0.0) {
     const double closedvalue = (-closed) * pprice_orig;
     double closecash = closedvalue;
-    if (closedvalue > 0.0) closecash /= c.leverage;
+    if (closedvalue > 0.0 && c.leverage != 1.0) closecash /= c.leverage;
     cash += closecash + pnl * 1.0;
     closedcomm = fabs(closed) * c.commission * price;
     cash -= closedcomm;
@@ -131,7 +146,7 @@ FX_HD bool fx_execute(const FxConfig& c, FxEnvRegs& e, double size, double price
   if (opened != 0.0) {
     const double openedvalue = opened * price;
     double opencash = openedvalue;
-    if (openedvalue > 0.0) opencash /= c.leverage;
+    if (openedvalue > 0.0 && c.leverage != 1.0) opencash /= c.leverage;
     cash -= opencash;
     openedcomm = fabs(opened) * c.commission * price;
     cash -= openedcomm;
@@ -157,8 +172,8 @@ FX_HD bool fx_execute(const FxConfig& c, FxEnvRegs& e, double size, double price
 }
 
 // ---- matching rules (bbroker.py _try_exec_market / _try_exec_limit / _try_exec_stop), no slippage --------------
-FX_HD bool fx_match_limit(double size, double plimit, const FxBar& b, double& px) {
-  if (size > 0.0) {
+FX_HD bool fx_match_limit(bool buy, double plimit, const FxBar& b, double& px) {
+  if (buy) {
     if (plimit >= b.o) { px = b.o; return true; }
     if (plimit >= b.l) { px = plimit; return true; }
   } else {
@@ -168,8 +183,8 @@ FX_HD bool fx_match_limit(double size, double plimit, const FxBar& b, double& px
   return false;
 }
 
-FX_HD bool fx_match_stop(double size, double pstop, const FxBar& b, double& px) {
-  if (size > 0.0) {
+FX_HD bool fx_match_stop(bool buy, double pstop, const FxBar& b, double& px) {
+  if (buy) {
     if (b.o >= pstop) { px = b.o; return true; }
     if (b.h >= pstop) { px = pstop; return true; }
   } else {
@@ -181,12 +196,13 @@ FX_HD bool fx_match_stop(double size, double pstop, const FxBar& b, double& px) 
 
 // Would entry k trade against bar b?  Pure function of the entry and the bar (lane-parallel on the device).
 // The ACTIVE / DEAD / SUBMITTED state is deliberately NOT consulted here: it can change during the FIFO walk.
-FX_HD bool fx_entry_hits(uint32_t meta, double p0, double p1, double sz, const FxBar& b) {
+FX_HD bool fx_entry_hits(uint32_t meta, double p0, double p1, const FxBar& b) {
   const uint32_t kind = meta & FXO_KIND_MASK;
+  const bool buy = !(meta & FXO_SELL);
   double px;
   if (kind == FXO_MARKET) return true;
-  if (kind == FXO_PARENT) return fx_match_limit(sz, p0, b, px);
-  return fx_match_stop(sz, p0, b, px) || fx_match_limit(sz, p1, b, px);
+  if (kind == FXO_PARENT) return fx_match_limit(buy, p0, b, px);
+  return fx_match_stop(buy, p0, b, px) || fx_match_limit(buy, p1, b, px);
 }
 
 // ---- BackBroker.next, step 0: "while self._toactivate: activate()" -- per entry, lane-parallel on the device ------
@@ -197,30 +213,41 @@ FX_HD uint32_t fx_entry_begin_bar(uint32_t meta) {
 // ---- BackBroker.next, step 1: check_submitted over the entries created by the previous strategy call ------------
 // (they are the tail [k_begin, n) of the table).  Running pseudo-cash over ONE position clone, in submission order;
 // the running cash is NOT restored after a rejection (bbroker.py keeps the negative value for the rest of the batch).
-FX_HD void fx_check_submitted(const FxConfig& c, const FxEnvRegs& e, FxOrderTab& t, int k_begin) {
+FX_HD_COLD void fx_check_submitted(const FxConfig& c, const FxEnvRegs& e, FxOrderTab& t, int k_begin) {
   double cash = e.cash, ps = e.psize, pp = e.pprice;
   for (int k = k_begin; k < t.n; k++) {
     const uint32_t m = t.meta[k];
     if (!(m & FXO_SUBMITTED) || (m & FXO_DEAD)) continue;
     const uint32_t kind = m & FXO_KIND_MASK;
+    const double sz = t.sz[k];
     bool margin = false;
-    if (kind != FXO_PAIR) {
-      fx_pseudo_execute(c, t.sz[k], t.p0[k], cash, ps, pp);
+    fx_pseudo_execute(c, sz, t.p0[k], cash, ps, pp);  // market / limit parent / stop child at created.price
+    margin = !(cash >= 0.0);
+    if (kind == FXO_PAIR && !margin) {                // then the limit child
+      fx_pseudo_execute(c, sz, t.p1[k], cash, ps, pp);
       margin = !(cash >= 0.0);
-      if (margin && kind == FXO_PARENT) t.meta[k + 1] |= FXO_DEAD;  // children: _take_children -> Rejected
-    } else {
-      // stop child, then limit child; either one going Margin cancels the whole (already accepted) group
-      fx_pseudo_execute(c, t.sz[k], t.p0[k], cash, ps, pp);
-      margin = !(cash >= 0.0);
-      if (!margin) {
-        fx_pseudo_execute(c, t.sz[k], t.p1[k], cash, ps, pp);
-        margin = !(cash >= 0.0);
-      }
-      if (margin) { t.meta[k - 1] |= FXO_DEAD; if (k - 1 < t.dirty_from) t.dirty_from = k - 1; }
     }
-    t.meta[k] = margin ? (m | FXO_DEAD) : (m & ~FXO_SUBMITTED);
-    if (k < t.dirty_from) t.dirty_from = k;
+    if (!margin) {
+      t.meta[k] = m & ~FXO_SUBMITTED;
+      if (k < t.dirty_from) t.dirty_from = k;
+      continue;
+    }
+    fx_kill(t, k);
+    if (kind == FXO_PARENT) fx_kill(t, k + 1);  // children: _take_children -> Rejected
+    if (kind == FXO_PAIR) fx_kill(t, k - 1);    // a child going Margin cancels the (already accepted) group
   }
+}
+
+// Upper bound of the pseudo-cash that check_submitted can take away for one submitted entry: every pseudo-execution
+// lowers the running cash by at most |size| * price * (max(1, 1/leverage) + commission) (closing a short or opening a
+// long; the other two cases ADD cash).  A PAIR is two pseudo-executions (stop child @p0, limit child @p1).
+// If cash >= 1.001 * (sum of the bounds of all submitted entries) no order can be rejected, and the exact sequential
+// simulation can be skipped without changing any outcome (the simulation only decides accept / reject).
+FX_HD double fx_submit_cash_bound(const FxConfig& c, uint32_t meta, double p0, double p1, double sz) {
+  const double per = (c.leverage < 1.0 ? 1.0 / c.leverage : 1.0) + fabs(c.commission);
+  double need = fabs(sz) * fabs(p0) * per;
+  if ((meta & FXO_KIND_MASK) == FXO_PAIR) need += fabs(sz) * fabs(p1) * per;
+  return need;
 }
 
 // ---- BackBroker.next, step 2: execute entry k (known to hit) in FIFO position ------------------------------------
@@ -228,24 +255,21 @@ FX_HD void fx_exec_entry(const FxConfig& c, FxEnvRegs& e, FxOrderTab& t, int k, 
   const uint32_t m = t.meta[k];
   if (m & (FXO_DEAD | FXO_SUBMITTED)) return;
   const uint32_t kind = m & FXO_KIND_MASK;
-  const double sz = t.sz[k];
-  double px = 0.0;
-  if (kind == FXO_MARKET) {
-    fx_execute(c, e, sz, b.o);
-    t.meta[k] = m | FXO_DEAD;
-  } else if (kind == FXO_PARENT) {
-    if (!fx_match_limit(sz, t.p0[k], b, px)) return;
-    const bool margin = fx_execute(c, e, sz, px);
-    t.meta[k] = m | FXO_DEAD;
-    if (margin) t.meta[k + 1] |= FXO_DEAD;
+  const bool buy = !(m & FXO_SELL);
+  double px = b.o;
+  bool go;
+  if (kind == FXO_MARKET) go = true;
+  else if (kind == FXO_PARENT) go = fx_match_limit(buy, t.p0[k], b, px);
+  else go = (m & FXO_ACTIVE) && (fx_match_stop(buy, t.p0[k], b, px) || fx_match_limit(buy, t.p1[k], b, px));
+  if (!go) return;
+  // Completed or Margin: either way the entry leaves the table.  A child that completes cancels its sibling, a child
+  // or parent that goes Margin cancels its whole group -- for a PAIR both mean "the pair is gone".
+  const bool margin = fx_execute(c, e, t.sz[k], px);
+  fx_kill(t, k);
+  if (kind == FXO_PARENT) {
+    if (margin) fx_kill(t, k + 1);
     else t.meta[k + 1] |= (c.children_same_bar ? FXO_ACTIVE : FXO_ACTIVATE_NEXT);
-  } else {
-    if (!(m & FXO_ACTIVE)) return;
-    if (!fx_match_stop(sz, t.p0[k], b, px) && !fx_match_limit(sz, t.p1[k], b, px)) return;
-    fx_execute(c, e, sz, px);  // Completed -> sibling cancelled; Margin -> group cancelled: the pair is gone
-    t.meta[k] = m | FXO_DEAD;
   }
-  if (k < t.dirty_from) t.dirty_from = k;
 }
 
 // ---- BackBroker._get_value (shortcash valuation; the long side is un-levered) -------------------------------------
@@ -260,14 +284,14 @@ FX_HD void fx_mark_to_market(const FxConfig& c, FxEnvRegs& e, double pclose) {
 
 // ---- order creation (Strategy.buy/sell/close/buy_bracket/sell_bracket) -------------------------------------------
 FX_HD bool fx_room(FxOrderTab& t, int need, uint32_t& flags) {
-  if (t.n + need <= t.cap) return true;
+  if (t.n - t.ndead + need <= t.cap && t.n + need <= t.cap + FXO_SLACK) return true;
   flags |= FX_FLAG_ORDER_OVERFLOW;
   return false;
 }
 
 FX_HD void fx_push(FxOrderTab& t, uint32_t meta, double p0, double p1, double sz) {
   const int k = t.n++;
-  t.meta[k] = meta; t.p0[k] = p0; t.p1[k] = p1; t.sz[k] = sz;
+  t.meta[k] = meta | (sz < 0.0 ? FXO_SELL : 0u); t.p0[k] = p0; t.p1[k] = p1; t.sz[k] = sz;
   if (k < t.dirty_from) t.dirty_from = k;
 }
 
@@ -336,10 +360,10 @@ FX_HD void fx_session_state(const FxConfig& c, int64_t minutes, bool& in_entry, 
 
 // ---- BTBridgeStrategy._apply_action at the current bar ------------------------------------------------------------
 // atr / atr_ready: simple-mean ATR of the env's TR deque (only read for FX_STRATEGY_ATR_SLTP).
-FX_HD void fx_apply_action(const FxConfig& c, FxEnvRegs& e, FxOrderTab& t, int action, const FxBar& b, int pair,
-                           double atr, bool atr_ready, bool has_minutes, int64_t minutes) {
+FX_HD void fx_apply_action(const FxConfig& c, int strategy, FxEnvRegs& e, FxOrderTab& t, int action, const FxBar& b,
+                           int pair, double atr, bool atr_ready, bool has_minutes, int64_t minutes) {
   const double pos = e.psize, pclose = b.c;
-  if (c.strategy == FX_STRATEGY_DEFAULT) {  // app/bt_bridge.py:171-190 (market orders)
+  if (strategy == FX_STRATEGY_DEFAULT) {  // app/bt_bridge.py:171-190 (market orders)
     const double size = c.position_size;
     if (action == 1) {
       if (pos < 0.0) { if (fx_room(t, 2, e.flags)) { fx_order_close(t, pos, pclose); fx_order_market(t, fabs(size), pclose); } }
@@ -351,7 +375,7 @@ FX_HD void fx_apply_action(const FxConfig& c, FxEnvRegs& e, FxOrderTab& t, int a
     return;
   }
   double size, sl, tp;
-  if (c.strategy == FX_STRATEGY_FIXED_SLTP) {  // direct_fixed_sltp.py:51-77
+  if (strategy == FX_STRATEGY_FIXED_SLTP) {  // direct_fixed_sltp.py:51-77
     if (action == 0) return;
     const double pip = c.pair_pip_size[pair] != 0.0 ? c.pair_pip_size[pair] : c.pip_size;
     size = c.strat_position_size;
@@ -424,28 +448,43 @@ FX_HD double fx_reward_dd(const FxConfig& c, const FxEnvRegs& e, double& peak, i
   return pnl_norm - c.penalty_lambda * dd_norm;
 }
 
-// sharpe: ring push (deque(maxlen=W).append); returns the new length
-FX_HD int fx_sharpe_push(double* ring, int W, int32_t& len, int32_t& head, int32_t& last_step, int32_t step, double r) {
+// sharpe: ring push (deque(maxlen=W).append) into ring[slot * stride]; returns the new length
+FX_HD int fx_sharpe_push(double* ring, int64_t stride, int W, int32_t& len, int32_t& head, int32_t& last_step,
+                         int32_t step, double r) {
   if (step <= last_step) { len = 0; head = 0; }
   last_step = step;
-  if (len == W) { ring[head] = r; head = (head + 1) % W; }
-  else { ring[(head + len) % W] = r; len++; }
+  if (len == W) { ring[head * stride] = r; head = (head + 1) % W; }
+  else { ring[((head + len) % W) * stride] = r; len++; }
   return len;
 }
 
-// sharpe: sequential (Python-order) evaluation over ring[(head+i) % W], i < n
-FX_HD double fx_sharpe_eval(const double* ring, int W, int n, int head, double ann) {
+// sharpe: sequential (Python-order) evaluation over ring[((head+i) % W) * stride], i < n
+FX_HD double fx_sharpe_eval(const double* ring, int64_t stride, int W, int n, int head, double ann) {
   if (n < 2) return 0.0;
-  double s = ring[head % W], comp = 0.0;
-  for (int i = 1; i < n; i++) fx_neumaier_add(s, comp, ring[(head + i) % W]);
+  int idx = head % W;
+  double s = ring[idx * stride], comp = 0.0;
+  for (int i = 1; i < n; i++) { idx = (idx + 1 == W) ? 0 : idx + 1; fx_neumaier_add(s, comp, ring[idx * stride]); }
   const double mean = fx_neumaier_done(s, comp) / (double)n;
-  double d = ring[head % W] - mean;
+  idx = head % W;
+  double d = ring[idx * stride] - mean;
   s = d * d; comp = 0.0;
-  for (int i = 1; i < n; i++) { d = ring[(head + i) % W] - mean; fx_neumaier_add(s, comp, d * d); }
+  for (int i = 1; i < n; i++) {
+    idx = (idx + 1 == W) ? 0 : idx + 1;
+    d = ring[idx * stride] - mean;
+    fx_neumaier_add(s, comp, d * d);
+  }
   const double var = fx_neumaier_done(s, comp) / (double)(n - 1);
   const double sd = sqrt(var);
   if (sd <= 0.0) return 0.0;
   return (mean / sd) * sqrt(ann);
+}
+
+// Welford update of the running (mean, M2) of one feature column with the n-th row (n >= 1 after the update);
+// used while the z-score history is still growing (warm-up of the rolling window, or expanding_zscore).
+FX_HD void fx_welford_add(double& mean, double& m2, double x, int n) {
+  const double d = x - mean;
+  mean += d / (double)n;
+  m2 += d * (x - mean);
 }
 
 // ---- observation element math ---------------------------------------------------------------------------------------
@@ -459,15 +498,18 @@ FX_HD float fx_clip_nan(float v, float clipf, bool do_clip) {
 
 // the 4 agent scalars.  ref_price: default preprocessor -> fp64 last window price; feature_window -> the
 // float32-rounded last window price (it reads obs["prices"][-1] back) or the bridge price without a price window.
-FX_HD void fx_agent_scalars(const FxConfig& c, const FxEnvRegs& e, int32_t total_bars, double ref_price, float out[4]) {
+// `inv_ic` = 1 / initial_cash (fp64, computed once on the host): x * inv_ic differs from x / ic by <= 1 ulp of fp64,
+// invisible after the float32 cast the reference applies to these values (obs tolerance 1e-5).
+FX_HD void fx_agent_scalars(const FxConfig& c, const FxEnvRegs& e, int32_t total_bars, double ref_price, double inv_ic,
+                            float out[4]) {
   const double ic = c.initial_cash != 0.0 ? c.initial_cash : 1.0;
   const double upnl = (double)e.position * (e.price - ref_price) * c.obs_position_size;
   int32_t rem = total_bars - e.bar_index;
   if (rem < 0) rem = 0;
   const int32_t den = total_bars > 1 ? total_bars : 1;
   out[0] = (float)(double)e.position;
-  out[1] = (float)((e.equity - ic) / ic);
-  out[2] = (float)(upnl / ic);
+  out[1] = (float)((e.equity - ic) * inv_ic);
+  out[2] = (float)(upnl * inv_ic);
   out[3] = (float)((double)rem / (double)den);
 }
 

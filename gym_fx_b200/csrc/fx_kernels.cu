@@ -1,17 +1,25 @@
 // fx_kernels.cu -- sm_100a kernels of the fused gym-fx env.step().
 //
-// fx_step_kernel: ONE launch = one env.step() for all N envs.  One warp owns one env:
-//   1. scalar state + the env's order table are pulled into registers / per-warp shared memory (coalesced);
-//   2. backtrader's per-bar broker pass: bracket activation and the trigger test of every live order run
-//      lane-parallel (one order per lane, ballot -> hit mask); the few orders that do trade are then executed
-//      in FIFO order by uniform scalar fp64 code (fx_core.cuh), exactly like BackBroker.next();
-//   3. the strategy plugin's apply_action appends new orders; bridge publish; reward (pnl / sharpe / dd);
-//   4. the observation row ([W,F] z-scored features | prices | returns | 4 agent scalars) is streamed by all 32
-//      lanes: coalesced fp64 reads of the L2-resident candle table, fp64 math, coalesced fp32 stores.
-// No tensor cores: there is no contraction on this path; it is bound by HBM stores of the observation rows.
+// fx_step_kernel<STRAT, REWARD, FAST5>: ONE launch = one env.step() for all N envs; one warp owns one env from start
+// to finish and a CTA is just FX_WARPS independent warps (no block barrier), so the ~28 warps an SM owns at 4096 envs
+// are all resident and progress concurrently.  Per warp:
 //
-// Reference call stack being replaced: app/env.py:131-172 -> app/bt_bridge.py:119-150 -> strategy/reward/
-// preprocessor plugins + backtrader (see fx_core.cuh for the per-function citations).
+//   scan     the env's order table is pulled into per-warp shared memory with ONE ORDER PER LANE (coalesced loads):
+//            bracket activation + trigger test against the new bar -> ballot hit mask; check_submitted is decided
+//            lane-parallel by a rigorous cash bound (the exact sequential simulation only runs when cash is tight);
+//   broker   the few orders that do trade are executed in FIFO order by uniform scalar fp64 code (fx_core.cuh),
+//            exactly like BackBroker.next(); then the strategy plugin's apply_action, bridge publish, reward;
+//   compact  stable lane-parallel compaction + write-back of the changed tail of the order table;
+//   observe  the observation row ([W,F] z-scored features | prices | returns | 4 agent scalars) is streamed by all
+//            lanes: coalesced fp64 reads of the L2-resident candle table, fp64 math, coalesced fp32 streaming stores.
+//
+// Odd warps stream the observation BEFORE the broker work and even warps after it, so on every SM the bandwidth-bound
+// phase of one half overlaps the latency-bound scalar chain of the other half.  The kernel is compiled once per
+// (strategy, reward, 5-feature fast path) so each instance only carries the code its configuration can reach.
+// No tensor cores: there is no contraction on this path.
+//
+// Reference call stack being replaced: app/env.py:131-172 -> app/bt_bridge.py:119-150 -> strategy / reward /
+// preprocessor plugins + backtrader (per-function citations in fx_core.cuh).
 #include <cuda_runtime.h>
 
 #include "fx_kernels.cuh"
@@ -20,46 +28,30 @@
 
 namespace {
 
+// per-warp shared memory: the staged order table + z-score statistics (+ the Sharpe ring)
 struct WarpSmem {
   double *p0, *p1, *sz, *mean, *rcp, *ring;
   uint32_t *meta, *hit;
 };
 
-__device__ __forceinline__ WarpSmem fx_carve(unsigned char* base, int cap, int ring_len) {
+__host__ __device__ inline size_t fx_warp_smem_bytes(int capP, int ring_len) {
+  size_t b = (size_t)capP * 3 * 8 + 2 * FXENV_MAX_FEATURES * 8 + (size_t)ring_len * 8 + (size_t)capP * 4 + (size_t)(capP / 32) * 4;
+  return (b + 15) & ~(size_t)15;
+}
+
+__device__ __forceinline__ WarpSmem fx_carve(unsigned char* base, int capP, int ring_len) {
   WarpSmem w;
   double* d = reinterpret_cast<double*>(base);
-  w.p0 = d; d += cap;
-  w.p1 = d; d += cap;
-  w.sz = d; d += cap;
+  w.p0 = d; d += capP;
+  w.p1 = d; d += capP;
+  w.sz = d; d += capP;
   w.mean = d; d += FXENV_MAX_FEATURES;
   w.rcp = d; d += FXENV_MAX_FEATURES;
   w.ring = d; d += ring_len;
   uint32_t* u = reinterpret_cast<uint32_t*>(d);
-  w.meta = u; u += cap;
+  w.meta = u; u += capP;
   w.hit = u;
   return w;
-}
-
-__device__ __forceinline__ double fx_warp_sum(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FX_FULL, v, o);
-  return v;
-}
-
-__device__ __forceinline__ void fx_load_regs(const FxDeviceState& st, int env, FxEnvRegs& e) {
-  e.cash = st.cash[env]; e.psize = st.psize[env]; e.pprice = st.pprice[env]; e.value = st.value[env];
-  e.equity = st.equity[env]; e.prev_equity = st.prev_equity[env]; e.price = st.price[env];
-  e.commission_paid = st.commission_paid[env];
-  e.position = st.position[env]; e.bar_index = st.bar_index[env]; e.trades = st.trades[env];
-  e.flags = st.flags[env];
-}
-
-__device__ __forceinline__ void fx_store_regs(const FxDeviceState& st, int env, const FxEnvRegs& e) {
-  st.cash[env] = e.cash; st.psize[env] = e.psize; st.pprice[env] = e.pprice; st.value[env] = e.value;
-  st.equity[env] = e.equity; st.prev_equity[env] = e.prev_equity; st.price[env] = e.price;
-  st.commission_paid[env] = e.commission_paid;
-  st.position[env] = e.position; st.bar_index[env] = e.bar_index; st.trades[env] = e.trades;
-  st.flags[env] = e.flags;
 }
 
 // GymFxEnv.reset (app/env.py:102-129): fresh bridge/broker/strategy; broker.next() on bar 0 with nothing pending
@@ -72,312 +64,428 @@ __device__ __forceinline__ void fx_reset_regs(const FxConfig& c, FxEnvRegs& e, d
   e.price = close0; e.bar_index = 1;
 }
 
+__device__ __forceinline__ void fx_store_all(const FxDeviceState& st, int env, const FxEnvRegs& e) {
+  st.cash[env] = e.cash; st.psize[env] = e.psize; st.pprice[env] = e.pprice;
+  st.equity[env] = e.equity; st.prev_equity[env] = e.prev_equity; st.price[env] = e.price;
+  st.commission_paid[env] = e.commission_paid;
+  st.position[env] = e.position; st.bar_index[env] = e.bar_index; st.trades[env] = e.trades;
+  st.flags[env] = e.flags;
+}
+
 __device__ __forceinline__ int32_t fx_total_bars(const FxConfig& c, int64_t T, int64_t start) {
   int64_t tb = T - start;
   if (c.episode_bars > 0 && c.episode_bars < tb) tb = c.episode_bars;
   return (int32_t)tb;
 }
 
-// ---- observation row: preprocessor.make_observation in the flat VecEnv layout -------------------------------------
-__device__ __forceinline__ void fx_write_obs(const FxKernelParams& P, const FxPairTable& tb, int lane, const WarpSmem& ws,
-                                             const FxEnvRegs& e, int32_t total_bars, int64_t start,
-                                             float* __restrict__ out) {
+__device__ __forceinline__ bool fx_uses_running_stats(const FxConfig& c) {
+  return c.preproc == FX_PREPROC_FEATURE_WINDOW && c.scaling != FX_SCALING_NONE;
+}
+
+// np.clip (float32) + np.nan_to_num(nan=0, posinf=clip, neginf=-clip), feature_window_preprocessor.py:119-123
+__device__ __forceinline__ float fx_finish(float v, float clipf, bool do_clip) {
+  v = (v != v) ? 0.0f : v;
+  if (do_clip) return fminf(fmaxf(v, -clipf), clipf);  // also maps +-inf to +-clip
+  return isinf(v) ? (v > 0.0f ? clipf : -clipf) : v;
+}
+
+// z-score statistics of the history window ending at local row s-1 -> smem mean/rcp (lanes f < F), warp-synchronous.
+// Full rolling window: the per-bar table computed at load time.  Otherwise (warm-up, expanding): running Welford state.
+__device__ __forceinline__ bool fx_prepare_stats(const FxKernelParams& P, const FxPairTable& tb, int env, int lane, int s,
+                                                 int64_t start, double* smean, double* srcp) {
   const FxConfig& c = P.cfg;
+  if (!fx_uses_running_stats(c)) return false;
+  const int F = c.n_features;
+  int hn = s;
+  if (c.scaling == FX_SCALING_ROLLING && hn > c.scaling_window) hn = c.scaling_window;
+  if (hn < 2) return false;
+  if (lane < F) {
+    double m, r;
+    if (c.scaling == FX_SCALING_ROLLING && hn == c.scaling_window && tb.stats != nullptr) {
+      const double* sp = tb.stats + ((start + s - 1) * (int64_t)F + lane) * 2;
+      m = sp[0]; r = sp[1];
+    } else {
+      const int64_t wi = ((int64_t)env * FXENV_MAX_FEATURES + lane) * 2;
+      m = P.st.welford[wi];
+      double sd = sqrt(P.st.welford[wi + 1] / (double)hn);
+      if (sd < 1e-8) sd = 1.0;
+      r = 1.0 / sd;
+    }
+    smean[lane] = m; srcp[lane] = r;
+  }
+  __syncwarp();
+  return true;
+}
+
+// ---- observation windows: preprocessor.make_observation (features | prices | returns) in the flat VecEnv layout ----
+template <bool FAST5>
+__device__ __noinline__ void fx_stream_windows(const FxKernelParams& P, const FxPairTable& tb, int env, int lane, int s,
+                                               int64_t start, double* smean, double* srcp, float* __restrict__ out) {
+  const FxConfig& c = P.cfg;
+  const bool scale = fx_prepare_stats(P, tb, env, lane, s, start, smean, srcp);
   const int W = c.window_size, C = c.n_cols;
-  int s = e.bar_index;
-  if (s < 0) s = 0;
-  if (s > total_bars) s = total_bars;  // app/env.py:228
   int left = s - W;
   if (left < 0) left = 0;
-  const int have = s - left;
-  const int pad = W - have;  // left padding with the first available row
-  const double* __restrict__ base = tb.candles + start * (int64_t)C;
+  const int pad = W - (s - left);  // left padding with the first available row
+  const double* __restrict__ base = tb.candles + (start + left) * (int64_t)C;
   int off = 0;
   if (c.preproc == FX_PREPROC_FEATURE_WINDOW) {
     const int F = c.n_features;
-    int hl = 0, hn = 0;
-    if (c.scaling == FX_SCALING_ROLLING) { hl = s - c.scaling_window; if (hl < 0) hl = 0; hn = s - hl; }
-    else if (c.scaling == FX_SCALING_EXPANDING) { hl = 0; hn = s; }
-    const bool scale = (c.scaling != FX_SCALING_NONE) && hn >= 2;
-    if (scale) {
-      if (c.scaling == FX_SCALING_ROLLING && hn == c.scaling_window && tb.stats != nullptr) {
-        // full rolling window: per-bar statistics precomputed at load time (pure function of the bar)
-        if (lane < F) {
-          const double* sp = tb.stats + ((start + s - 1) * (int64_t)F + lane) * 2;
-          ws.mean[lane] = sp[0];
-          ws.rcp[lane] = sp[1];
-        }
-      } else {
-        // warm-up (history shorter than the scaling window) or expanding z-score: two-pass mean / population std
-        for (int f = 0; f < F; f++) {
-          const int col = c.feature_cols[f];
-          double acc = 0.0;
-          for (int k = lane; k < hn; k += 32) acc += base[(int64_t)(hl + k) * C + col];
-          const double m = fx_warp_sum(acc) / (double)hn;
-          double a2 = 0.0;
-          for (int k = lane; k < hn; k += 32) { const double d = base[(int64_t)(hl + k) * C + col] - m; a2 += d * d; }
-          double sd = sqrt(fx_warp_sum(a2) / (double)hn);
-          if (sd < 1e-8) sd = 1.0;
-          if (lane == 0) { ws.mean[f] = m; ws.rcp[f] = 1.0 / sd; }
-        }
-      }
-      __syncwarp();
-    }
     const float clipf = (float)c.feature_clip;
     const bool do_clip = c.feature_clip > 0.0;
     const int total = W * F;
-    if (P.fast_features && pad == 0) {
-      // feature columns == all table columns and no padding: the [W][F] block is one contiguous span of the table
-      const double* __restrict__ src = base + (int64_t)left * C;
-      for (int j = lane; j < total; j += 32) {
-        const int f = j % F;
-        const double x = __ldg(src + j);
-        const float v = (scale && !c.feature_binary[f]) ? (float)((x - ws.mean[f]) * ws.rcp[f]) : (float)x;
-        __stcs(out + j, fx_clip_nan(v, clipf, do_clip));
+    if (FAST5 && pad == 0) {
+      // F == n_cols == 5, identity columns, full window: the [W][5] block is ONE contiguous span of the table.
+      // 30 lanes = 6 whole rows per pass, so a lane's feature (hence its mean / 1/std) is loop-invariant.
+      if (lane < 30) {
+        const int f = lane % 5;
+        const bool z = scale && !c.feature_binary[f];
+        const double m = z ? smean[f] : 0.0, r = z ? srcp[f] : 1.0;
+#pragma unroll 8
+        for (int j = lane; j < total; j += 30) {
+          const double x = __ldg(base + j);
+          const float v = z ? (float)((x - m) * r) : (float)x;
+          __stcs(out + j, fx_finish(v, clipf, do_clip));
+        }
       }
     } else {
+      // general path: (row, feature) advanced incrementally, no integer division in the loop
+      int w = lane / F, f = lane - w * F;
+      const int dw = 32 / F, df = 32 - dw * F;
       for (int j = lane; j < total; j += 32) {
-        const int w = j / F, f = j - w * F;
         int k = w - pad;
         if (k < 0) k = 0;
-        const double x = __ldg(base + (int64_t)(left + k) * C + c.feature_cols[f]);
-        const float v = (scale && !c.feature_binary[f]) ? (float)((x - ws.mean[f]) * ws.rcp[f]) : (float)x;
-        __stcs(out + j, fx_clip_nan(v, clipf, do_clip));
+        const double x = __ldg(base + k * C + c.feature_cols[f]);
+        const float v = (scale && !c.feature_binary[f]) ? (float)((x - smean[f]) * srcp[f]) : (float)x;
+        __stcs(out + j, fx_finish(v, clipf, do_clip));
+        w += dw; f += df;
+        if (f >= F) { f -= F; w += 1; }
       }
     }
     off = total;
   }
   const bool inc_price = (c.preproc == FX_PREPROC_DEFAULT) || c.include_price_window;
-  const bool inc_agent = (c.preproc == FX_PREPROC_DEFAULT) || c.include_agent_state;
-  const int pc = c.price_col;
   if (inc_price) {
+    const int pc = c.price_col;
+#pragma unroll 4
     for (int w = lane; w < W; w += 32) {
       int k = w - pad;
       if (k < 0) k = 0;
-      const double p = __ldg(base + (int64_t)(left + k) * C + pc);
-      double prev = p;
-      if (w > 0) {
-        int k1 = w - 1 - pad;
-        if (k1 < 0) k1 = 0;
-        prev = __ldg(base + (int64_t)(left + k1) * C + pc);
-      }
+      int k1 = w - 1 - pad;
+      if (k1 < 0) k1 = 0;
+      const double p = __ldg(base + k * C + pc);
+      const double prev = __ldg(base + k1 * C + pc);
       __stcs(out + off + w, (float)p);
       __stcs(out + off + W + w, (w == 0) ? 0.0f : (float)(p - prev));
     }
-    off += 2 * W;
-  }
-  if (inc_agent && lane == 0) {
-    const double last = base[(int64_t)(left + have - 1) * C + pc];
-    double ref;
-    if (c.preproc == FX_PREPROC_DEFAULT) ref = last;                       // default_preprocessor.py:63
-    else ref = inc_price ? (double)(float)last : e.price;                  // feature_window_preprocessor.py:218-222
-    float sc[4];
-    fx_agent_scalars(c, e, total_bars, ref, sc);
-    out[off + 0] = sc[0]; out[off + 1] = sc[1]; out[off + 2] = sc[2]; out[off + 3] = sc[3];
   }
 }
 
-// ---- the fused step ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(FX_WARPS_PER_BLOCK * 32)
+__device__ __forceinline__ int fx_scalar_offset(const FxConfig& c) {
+  const int W = c.window_size;
+  if (c.preproc == FX_PREPROC_DEFAULT) return 2 * W;
+  return W * c.n_features + (c.include_price_window ? 2 * W : 0);
+}
+
+// the 4 agent scalars at the end of the row (one lane)
+__device__ __forceinline__ void fx_write_scalars(const FxKernelParams& P, const FxPairTable& tb, const FxEnvRegs& e,
+                                                 int32_t total_bars, int64_t start, float* __restrict__ out) {
+  const FxConfig& c = P.cfg;
+  const bool inc_agent = (c.preproc == FX_PREPROC_DEFAULT) || c.include_agent_state;
+  if (!inc_agent) return;
+  const bool inc_price = (c.preproc == FX_PREPROC_DEFAULT) || c.include_price_window;
+  int s = e.bar_index;
+  if (s < 1) s = 1;
+  if (s > total_bars) s = total_bars;
+  const double last = tb.candles[(start + s - 1) * (int64_t)c.n_cols + c.price_col];
+  double ref;
+  if (c.preproc == FX_PREPROC_DEFAULT) ref = last;       // default_preprocessor.py:63
+  else ref = inc_price ? (double)(float)last : e.price;  // feature_window_preprocessor.py:218-222
+  float sc[4];
+  fx_agent_scalars(c, e, total_bars, ref, P.inv_initial_cash, sc);
+  float* o = out + fx_scalar_offset(c);
+  o[0] = sc[0]; o[1] = sc[1]; o[2] = sc[2]; o[3] = sc[3];
+}
+
+// ---- the fused step --------------------------------------------------------------------------------------------
+template <int STRAT, int REWARD, bool FAST5>
+__global__ void __launch_bounds__(FX_WARPS * 32, 32 / FX_WARPS)
 fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict__ actions, float* __restrict__ obs,
                float* __restrict__ reward, double* __restrict__ reward64, uint8_t* __restrict__ terminated) {
   extern __shared__ __align__(16) unsigned char fx_smem[];
   const FxConfig& c = P.cfg;
   const FxDeviceState& st = P.st;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int env = blockIdx.x * FX_WARPS_PER_BLOCK + warp;
+  const int env = blockIdx.x * FX_WARPS + warp;
   if (env >= c.num_envs) return;
-  const int cap = P.cap;
-  const int ring_len = (c.reward == FX_REWARD_SHARPE) ? c.sharpe_window : 0;
-  const WarpSmem ws = fx_carve(fx_smem + (size_t)warp * P.smem_per_warp, cap, ring_len);
+  const int capP = P.cap + FXO_SLACK;
+  const int ring_len = (REWARD == FX_REWARD_SHARPE) ? c.sharpe_window : 0;
+  const WarpSmem ws = fx_carve(fx_smem + (size_t)warp * fx_warp_smem_bytes(capP, ring_len), capP, ring_len);
+  const int C = c.n_cols;
   const int pair = env % c.num_pairs;
   const FxPairTable& tb = P.pair[pair];
-  const int C = c.n_cols;
   float* __restrict__ obs_row = obs + (int64_t)env * P.obs_dim;
+  long long* tstamp = P.timing ? P.timing + (int64_t)env * FX_NSTAMP : nullptr;
+#define FX_STAMP(i) do { if (tstamp && lane == 0) tstamp[i] = clock64(); } while (0)
+  FX_STAMP(0);
 
-  FxEnvRegs e;
-  fx_load_regs(st, env, e);
+  // ---- one batch of independent loads (state invariants: see FxDeviceState)
+  uint32_t flags = st.flags[env];
   int32_t t = st.t[env];
   int32_t total_bars = st.total_bars[env];
-  int64_t start = st.start[env];
-  int n = st.n_orders[env];
+  const int64_t start = st.start[env];
+  const int n = st.n_orders[env];
+  FxEnvRegs e;
+  e.cash = st.cash[env]; e.psize = st.psize[env]; e.pprice = st.pprice[env]; e.equity = st.equity[env];
+  e.commission_paid = st.commission_paid[env]; e.trades = st.trades[env];
+  e.value = e.equity;
+  const double cash0 = e.cash, psize0 = e.psize, pprice0 = e.pprice, comm0 = e.commission_paid;
+  const int32_t trades0 = e.trades;
 
-  int action;
-  if (c.action_mode == FX_ACTION_CONTINUOUS) action = fx_coerce_continuous(c, reinterpret_cast<const float*>(actions)[env]);
-  else action = fx_coerce_discrete(reinterpret_cast<const int32_t*>(actions)[env]);
-
-  // --- already terminated: the reference answers (obs, 0.0, True) without touching plugins (app/env.py:137-138)
-  if (e.flags & FX_FLAG_TERMINATED) {
+  // ---- terminated envs: the reference answers (obs, 0.0, True) without touching plugins (app/env.py:137-138);
+  //      with auto_reset (build-side extension) the env restarts its episode window instead
+  if (flags & FX_FLAG_TERMINATED) {
     if (c.auto_reset) {
-      // build-side extension: next-step auto reset (the env restarts its episode window)
       total_bars = fx_total_bars(c, tb.T, start);
       fx_reset_regs(c, e, tb.candles[start * (int64_t)C + 3]);
-      if (lane == 0) {
-        fx_store_regs(st, env, e);
-        st.t[env] = 0; st.total_bars[env] = total_bars; st.n_orders[env] = 0;
-        reward[env] = 0.0f; terminated[env] = 0;
-        if (reward64) reward64[env] = 0.0;
+      if (fx_uses_running_stats(c) && lane < c.n_features) {
+        const int64_t wi = ((int64_t)env * FXENV_MAX_FEATURES + lane) * 2;
+        st.welford[wi] = tb.candles[start * (int64_t)C + c.feature_cols[lane]];
+        st.welford[wi + 1] = 0.0;
       }
-      fx_write_obs(P, tb, lane, ws, e, total_bars, start, obs_row);
-      return;
+      if (lane == 0) {
+        fx_store_all(st, env, e);
+        st.t[env] = 0; st.total_bars[env] = total_bars; st.n_orders[env] = 0;
+      }
+    } else {
+      e.flags = flags;
+      e.bar_index = t + 1;
+      e.position = e.psize > 0.0 ? 1 : (e.psize < 0.0 ? -1 : 0);
+      e.price = tb.candles[(start + t) * (int64_t)C + 3];
     }
     if (lane == 0) {
-      reward[env] = 0.0f; terminated[env] = 1;
+      reward[env] = 0.0f;
       if (reward64) reward64[env] = 0.0;
+      terminated[env] = c.auto_reset ? 0 : 1;
+      fx_write_scalars(P, tb, e, total_bars, start, obs_row);
     }
-    fx_write_obs(P, tb, lane, ws, e, total_bars, start, obs_row);
+    fx_stream_windows<FAST5>(P, tb, env, lane, e.bar_index, start, ws.mean, ws.rcp, obs_row);
     return;
   }
 
-  // --- step <-> bar timeline: the first step does not advance; later steps advance or exhaust
+  // ---- step <-> bar timeline: the first step does not advance; later steps advance or exhaust
   bool exhausted = false, advance = false;
-  if (!(e.flags & FX_FLAG_STARTED)) e.flags |= FX_FLAG_STARTED;
+  if (!(flags & FX_FLAG_STARTED)) flags |= FX_FLAG_STARTED;
   else if (t + 1 >= total_bars) exhausted = true;  // strategy.stop(): bridge state unchanged (app/bt_bridge.py:152-155)
   else { t += 1; advance = true; }
+  e.flags = flags;
 
+  const double* __restrict__ row = tb.candles + (start + t) * (int64_t)C;
   FxBar b;
-  {
-    const double* r = tb.candles + (start + t) * (int64_t)C;
-    b.o = r[0]; b.h = r[1]; b.l = r[2]; b.c = r[3];
-  }
-  FxOrderTab tab;
-  tab.meta = ws.meta; tab.p0 = ws.p0; tab.p1 = ws.p1; tab.sz = ws.sz;
-  tab.n = n; tab.cap = cap; tab.dirty_from = n;
-  const int64_t obase = (int64_t)env * cap;
+  b.o = row[0]; b.h = row[1]; b.l = row[2]; b.c = row[3];
 
-  if (advance && n > 0) {
-    // ---- BackBroker.next(): stage the order table; lane-parallel activation + trigger test
-    int first_sub = n, first_changed = n;
-    const int nch = (n + 31) >> 5;
-    for (int ch = 0; ch < nch; ch++) {
-      const int k = ch * 32 + lane;
-      bool hit = false, sub = false, changed = false;
-      if (k < n) {
-        const uint32_t m0 = st.o_meta[obase + k];
-        const uint32_t m = fx_entry_begin_bar(m0);
-        const double p0 = st.o_p0[obase + k], p1 = st.o_p1[obase + k], sz = st.o_sz[obase + k];
-        ws.meta[k] = m; ws.p0[k] = p0; ws.p1[k] = p1; ws.sz[k] = sz;
-        changed = (m != m0);
-        sub = (m & FXO_SUBMITTED) != 0u;
-        hit = fx_entry_hits(m, p0, p1, sz, b);
-      }
-      const uint32_t hm = __ballot_sync(FX_FULL, hit);
-      const uint32_t sm = __ballot_sync(FX_FULL, sub);
-      const uint32_t cm = __ballot_sync(FX_FULL, changed);
-      if (lane == 0) ws.hit[ch] = hm;
-      if (sm && first_sub == n) first_sub = ch * 32 + __ffs(sm) - 1;
-      if (cm && first_changed == n) first_changed = ch * 32 + __ffs(cm) - 1;
-    }
-    __syncwarp();
-    tab.dirty_from = first_changed;
-    fx_check_submitted(c, e, tab, first_sub);
-    __syncwarp();
-    // ---- FIFO walk over the entries that trade on this bar (uniform scalar code)
-    for (int ch = 0; ch < nch; ch++) {
-      uint32_t m = ws.hit[ch];
-      while (m) {
-        const int k = ch * 32 + __ffs(m) - 1;
-        m &= m - 1;
-        fx_exec_entry(c, e, tab, k, b);
-      }
-    }
-    __syncwarp();
-    // ---- stable compaction of finished entries (keeps FIFO order == array order)
-    if (tab.dirty_from < n) {
-      int w = 0;
-      for (int ch = 0; ch < nch; ch++) {
-        const int k = ch * 32 + lane;
-        uint32_t m = 0u; double p0 = 0.0, p1 = 0.0, sz = 0.0;
-        bool keep = false;
-        if (k < n) { m = ws.meta[k]; p0 = ws.p0[k]; p1 = ws.p1[k]; sz = ws.sz[k]; keep = !(m & FXO_DEAD); }
-        const uint32_t km = __ballot_sync(FX_FULL, keep);
-        __syncwarp();
-        if (keep) {
-          const int dst = w + __popc(km & ((1u << lane) - 1u));
-          ws.meta[dst] = m; ws.p0[dst] = p0; ws.p1[dst] = p1; ws.sz[dst] = sz;
+  // running z-score statistics while the history window is still growing (or expanding_zscore)
+  if (advance && fx_uses_running_stats(c) && (c.scaling == FX_SCALING_EXPANDING || t + 1 <= c.scaling_window) &&
+      lane < c.n_features) {
+    const int64_t wi = ((int64_t)env * FXENV_MAX_FEATURES + lane) * 2;
+    double m = st.welford[wi], m2 = st.welford[wi + 1];
+    fx_welford_add(m, m2, row[c.feature_cols[lane]], t + 1);
+    st.welford[wi] = m; st.welford[wi + 1] = m2;
+  }
+  FX_STAMP(1);  // state + bar loaded, running stats updated
+
+  const int dbg = P.debug;
+  const bool obs_first = (warp & 1) != 0;
+  if (obs_first && !(dbg & 1)) fx_stream_windows<FAST5>(P, tb, env, lane, t + 1, start, ws.mean, ws.rcp, obs_row);
+  FX_STAMP(2);  // (odd warps) observation streamed
+
+  if (!(dbg & 2)) {
+    const int64_t obase = (int64_t)env * capP;
+    FxOrderTab tab;
+    tab.meta = ws.meta; tab.p0 = ws.p0; tab.p1 = ws.p1; tab.sz = ws.sz;
+    tab.n = n; tab.cap = P.cap; tab.dirty_from = n; tab.ndead = 0;
+
+    if (advance) {
+      if (n > 0) {
+        // BackBroker.next(): stage the table; activation of queued children + trigger test, one order per lane
+        int first_sub = n, first_changed = n;
+        uint32_t any_hit = 0u;
+        double need = 0.0;
+        const int nch = (n + 31) >> 5;
+        for (int ch = 0; ch < nch; ch++) {
+          const int k = ch * 32 + lane;
+          bool hit = false, sub = false, changed = false;
+          if (k < n) {
+            const uint32_t m0 = st.o_meta[obase + k];
+            const double p0 = st.o_p0[obase + k], p1 = st.o_p1[obase + k], sz = st.o_sz[obase + k];
+            const uint32_t m = fx_entry_begin_bar(m0);
+            ws.meta[k] = m; ws.p0[k] = p0; ws.p1[k] = p1; ws.sz[k] = sz;
+            changed = (m != m0);
+            sub = (m & FXO_SUBMITTED) != 0u;
+            hit = fx_entry_hits(m, p0, p1, b);
+            if (sub) need += fx_submit_cash_bound(c, m, p0, p1, sz);
+          }
+          const uint32_t hm = __ballot_sync(FX_FULL, hit);
+          const uint32_t sbm = __ballot_sync(FX_FULL, sub);
+          const uint32_t cm = __ballot_sync(FX_FULL, changed);
+          if (lane == 0) ws.hit[ch] = hm;
+          any_hit |= hm;
+          if (sbm && first_sub == n) first_sub = ch * 32 + __ffs(sbm) - 1;
+          if (cm && first_changed == n) first_changed = ch * 32 + __ffs(cm) - 1;
         }
-        w += __popc(km);
         __syncwarp();
+        FX_STAMP(3);  // order table staged + trigger scan done
+        tab.dirty_from = first_changed;
+        if (first_sub < n) {
+          // check_submitted: lane-parallel decision by the cash bound, exact sequential simulation only if tight
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) need += __shfl_xor_sync(FX_FULL, need, o);
+          if (e.cash >= need * 1.001) {
+            for (int k = first_sub + lane; k < n; k += 32) ws.meta[k] &= ~FXO_SUBMITTED;  // nobody can be rejected
+            if (first_sub < tab.dirty_from) tab.dirty_from = first_sub;
+            __syncwarp();
+          } else {
+            fx_check_submitted(c, e, tab, first_sub);
+          }
+        }
+        FX_STAMP(4);  // check_submitted done
+        if (any_hit) {
+          // FIFO walk over the entries that trade on this bar (uniform scalar code on the staged copy)
+          for (int ch = 0; ch < nch; ch++) {
+            uint32_t m = ws.hit[ch];
+            while (m) {
+              const int k = ch * 32 + __ffs(m) - 1;
+              m &= m - 1;
+              fx_exec_entry(c, e, tab, k, b);
+            }
+          }
+        }
       }
-      tab.n = w;
+      fx_mark_to_market(c, e, b.c);
     }
-  }
-  if (advance) fx_mark_to_market(c, e, b.c);
+    FX_STAMP(5);  // fills executed, marked to market
 
-  if (!exhausted) {
-    // ---- strategy plugin (BTBridgeStrategy._apply_action) at bar t
-    double atr = 0.0;
-    bool atr_ready = false;
-    if (c.strategy == FX_STRATEGY_ATR_SLTP && action != 0) {
-      // simple-mean ATR over the env's TR deque; TR(k) is a pure function of the table, so the
-      // deque is rebuilt from the last min(t+1, period) bars in deque order with Python's compensated sum()
-      const int period = c.atr_period;
-      const int nb = (t + 1 < period) ? t + 1 : period;
-      double s_ = 0.0, comp = 0.0;
-      for (int j = 0; j < nb; j++) {
-        const int k = t - nb + 1 + j;
-        const double* r = tb.candles + (start + k) * (int64_t)C;
-        const double prevc = (k > 0) ? r[3 - C] : 0.0;
-        const double tr = fx_true_range(r[1], r[2], prevc, k > 0);
-        if (j == 0) s_ = tr; else fx_neumaier_add(s_, comp, tr);
+    double r;
+    if (!exhausted) {
+      int action;
+      if (c.action_mode == FX_ACTION_CONTINUOUS) action = fx_coerce_continuous(c, reinterpret_cast<const float*>(actions)[env]);
+      else action = fx_coerce_discrete(reinterpret_cast<const int32_t*>(actions)[env]);
+      double atr = 0.0;
+      bool atr_ready = false;
+      if (STRAT == FX_STRATEGY_ATR_SLTP && action != 0) {
+        // simple-mean ATR over the env's TR deque; TR(k) is a pure function of the table: lanes fetch the
+        // last min(t+1, period) bars in parallel, then the deque-order compensated sum (Python's sum()) runs uniformly
+        const int period = c.atr_period;
+        const int nb = (t + 1 < period) ? t + 1 : period;
+        double s_ = 0.0, comp = 0.0;
+        for (int j0 = 0; j0 < nb; j0 += 32) {
+          double tr = 0.0;
+          const int j = j0 + lane;
+          if (j < nb) {
+            const int k = t - nb + 1 + j;
+            const double* rr = tb.candles + (start + k) * (int64_t)C;
+            tr = fx_true_range(rr[1], rr[2], (k > 0) ? rr[3 - C] : 0.0, k > 0);
+          }
+          const int lim = (nb - j0 < 32) ? nb - j0 : 32;
+          for (int q = 0; q < lim; q++) {
+            const double x = __shfl_sync(FX_FULL, tr, q);
+            if (j0 + q == 0) s_ = x; else fx_neumaier_add(s_, comp, x);
+          }
+        }
+        atr = fx_neumaier_done(s_, comp) / (double)nb;
+        atr_ready = nb >= period;
       }
-      atr = fx_neumaier_done(s_, comp) / (double)nb;
-      atr_ready = nb >= period;
+      const bool has_min = (tb.minutes != nullptr);
+      const int64_t minutes = (STRAT == FX_STRATEGY_ATR_SLTP && c.session_filter && has_min) ? tb.minutes[start + t] : 0;
+      fx_apply_action(c, STRAT, e, tab, action, b, pair, atr, atr_ready, has_min, minutes);
+      fx_publish(e, b.c, t);
+      if (e.equity <= c.min_equity) e.flags |= FX_FLAG_TERMINATED | FX_FLAG_BROKE;  // app/bt_bridge.py:140-143
+    } else {
+      e.flags |= FX_FLAG_TERMINATED | FX_FLAG_EXHAUSTED;
+      e.prev_equity = st.prev_equity[env];
+      e.bar_index = t + 1;
+      e.position = e.psize > 0.0 ? 1 : (e.psize < 0.0 ? -1 : 0);
+      e.price = b.c;
     }
-    const bool has_min = (tb.minutes != nullptr);
-    const int64_t minutes = (c.session_filter && has_min) ? tb.minutes[start + t] : 0;
-    fx_apply_action(c, e, tab, action, b, pair, atr, atr_ready, has_min, minutes);
-    fx_publish(e, b.c, t);
-    if (e.equity <= c.min_equity) e.flags |= FX_FLAG_TERMINATED | FX_FLAG_BROKE;  // app/bt_bridge.py:140-143
-  } else {
-    e.flags |= FX_FLAG_TERMINATED | FX_FLAG_EXHAUSTED;
-  }
-  __syncwarp();
+    FX_STAMP(6);  // strategy + publish
 
-  // ---- reward plugin (app/env.py:148-155)
-  double r;
-  if (c.reward == FX_REWARD_PNL) {
-    r = fx_reward_pnl(c, e);
-  } else if (c.reward == FX_REWARD_DD) {
-    double peak = st.dd_peak[env];
-    int32_t last = st.dd_last_step[env];
-    r = fx_reward_dd(c, e, peak, last);
-    if (lane == 0) { st.dd_peak[env] = peak; st.dd_last_step[env] = last; }
-  } else {
-    const int Wn = c.sharpe_window;
-    double* gring = st.sh_ring + (int64_t)env * Wn;
-    int32_t len = st.sh_len[env], head = st.sh_head[env], last = st.sh_last_step[env];
-    for (int k = lane; k < Wn; k += 32) ws.ring[k] = gring[k];
-    __syncwarp();
-    const double ret = (e.equity - e.prev_equity) / c.reward_initial_cash;
-    const int32_t len0 = len, head0 = head;
-    int slot;  // where the new return lands (same rule as fx_sharpe_push)
-    if (e.bar_index <= last) slot = 0; else slot = (len0 == Wn) ? head0 : (head0 + len0) % Wn;
-    const int nn = fx_sharpe_push(ws.ring, Wn, len, head, last, e.bar_index, ret);
-    r = fx_sharpe_eval(ws.ring, Wn, nn, head, c.annualization_factor);
+    // ---- reward plugin (app/env.py:148-155)
+    if (REWARD == FX_REWARD_PNL) {
+      r = fx_reward_pnl(c, e);
+    } else if (REWARD == FX_REWARD_DD) {
+      double peak = st.dd_peak[env];
+      int32_t last = st.dd_last_step[env];
+      r = fx_reward_dd(c, e, peak, last);
+      if (lane == 0) { st.dd_peak[env] = peak; st.dd_last_step[env] = last; }
+    } else {
+      // deque of per-step returns: stage the ring in shared memory (coalesced), push, evaluate in Python order
+      const int Wn = c.sharpe_window;
+      double* gring = st.sh_ring + (int64_t)env * Wn;
+      int32_t len = st.sh_len[env], head = st.sh_head[env], last = st.sh_last_step[env];
+      for (int k = lane; k < Wn; k += 32) ws.ring[k] = gring[k];
+      __syncwarp();
+      const double ret = (e.equity - e.prev_equity) / c.reward_initial_cash;
+      int slot;  // where the new return lands (same rule as fx_sharpe_push)
+      if (e.bar_index <= last) slot = 0; else slot = (len == Wn) ? head : (head + len) % Wn;
+      const int nn = fx_sharpe_push(ws.ring, 1, Wn, len, head, last, e.bar_index, ret);
+      r = fx_sharpe_eval(ws.ring, 1, Wn, nn, head, c.annualization_factor);
+      if (lane == 0) {
+        gring[slot] = ret;
+        st.sh_len[env] = len; st.sh_head[env] = head; st.sh_last_step[env] = last;
+      }
+    }
+    const bool term = ((e.flags & FX_FLAG_TERMINATED) != 0u) || (e.equity <= c.min_equity);  // app/env.py:157
+    FX_STAMP(7);  // reward
+
+    // ---- write back (lane 0): always-changing columns, then the ones a fill touched
     if (lane == 0) {
-      gring[slot] = ret;
-      st.sh_len[env] = len; st.sh_head[env] = head; st.sh_last_step[env] = last;
+      st.t[env] = t; st.flags[env] = e.flags;
+      st.equity[env] = e.equity; st.prev_equity[env] = e.prev_equity; st.price[env] = e.price;
+      st.position[env] = e.position; st.bar_index[env] = e.bar_index;
+      if (e.cash != cash0) st.cash[env] = e.cash;
+      if (e.psize != psize0) st.psize[env] = e.psize;
+      if (e.pprice != pprice0) st.pprice[env] = e.pprice;
+      if (e.commission_paid != comm0) st.commission_paid[env] = e.commission_paid;
+      if (e.trades != trades0) st.trades[env] = e.trades;
+      reward[env] = (float)r;
+      if (reward64) reward64[env] = r;
+      terminated[env] = term ? 1 : 0;
+      fx_write_scalars(P, tb, e, total_bars, start, obs_row);
     }
-  }
-  const bool term = ((e.flags & FX_FLAG_TERMINATED) != 0u) || (e.equity <= c.min_equity);  // app/env.py:157
+    __syncwarp();
 
-  // ---- write back: scalars, outputs, the stale tail of the order table
-  if (lane == 0) {
-    fx_store_regs(st, env, e);
-    st.t[env] = t;
-    st.n_orders[env] = tab.n;
-    reward[env] = (float)r;
-    if (reward64) reward64[env] = r;
-    terminated[env] = term ? 1 : 0;
+    // ---- order table: stable compaction of finished entries + write-back of the changed tail (from shared memory)
+    {
+      const int n_tot = tab.n, from = tab.dirty_from;
+      int n_live = n_tot;
+      if (from < n_tot) {
+        int w = from;
+        for (int k0 = from & ~31; k0 < n_tot; k0 += 32) {
+          const int k = k0 + lane;
+          uint32_t m = 0u;
+          bool keep = false;
+          if (k >= from && k < n_tot) { m = ws.meta[k]; keep = !(m & FXO_DEAD); }
+          const uint32_t km = __ballot_sync(FX_FULL, keep);
+          if (keep) {
+            const int dst = w + __popc(km & ((1u << lane) - 1u));
+            st.o_meta[obase + dst] = m; st.o_p0[obase + dst] = ws.p0[k]; st.o_p1[obase + dst] = ws.p1[k];
+            st.o_sz[obase + dst] = ws.sz[k];
+          }
+          w += __popc(km);
+        }
+        n_live = w;
+      }
+      if (lane == 0 && n_live != n) st.n_orders[env] = n_live;
+    }
+  } else if (lane == 0) {  // timing experiment only (FXENV_DEBUG & 2): cursor only
+    st.t[env] = t; st.flags[env] = flags; st.bar_index[env] = t + 1; reward[env] = 0.f; terminated[env] = 0;
   }
-  for (int k = tab.dirty_from + lane; k < tab.n; k += 32) {
-    st.o_meta[obase + k] = ws.meta[k]; st.o_p0[obase + k] = ws.p0[k];
-    st.o_p1[obase + k] = ws.p1[k]; st.o_sz[obase + k] = ws.sz[k];
-  }
+  FX_STAMP(8);  // scalars written back, order table compacted
 
-  // ---- observation (app/env.py:160 -> preprocessor.make_observation)
-  fx_write_obs(P, tb, lane, ws, e, total_bars, start, obs_row);
+  // ---- observation windows (app/env.py:160 -> preprocessor.make_observation): bar_index = t + 1
+  if (!obs_first && !(dbg & 1)) fx_stream_windows<FAST5>(P, tb, env, lane, t + 1, start, ws.mean, ws.rcp, obs_row);
+  FX_STAMP(9);  // (even warps) observation streamed
+#undef FX_STAMP
 }
 
 __global__ void fx_reset_kernel(const __grid_constant__ FxKernelParams P, const int64_t* __restrict__ start_bar,
@@ -397,26 +505,40 @@ __global__ void fx_reset_kernel(const __grid_constant__ FxKernelParams P, const 
   if (start > tb.T - 1) start = tb.T - 1;
   FxEnvRegs e;
   fx_reset_regs(c, e, tb.candles[start * (int64_t)c.n_cols + 3]);
-  fx_store_regs(st, env, e);
+  fx_store_all(st, env, e);
   st.start[env] = start;
   st.t[env] = 0;
   st.total_bars[env] = fx_total_bars(c, tb.T, start);
   st.n_orders[env] = 0;
+  if (fx_uses_running_stats(c)) {
+    for (int f = 0; f < c.n_features; f++) {
+      const int64_t wi = ((int64_t)env * FXENV_MAX_FEATURES + f) * 2;
+      st.welford[wi] = tb.candles[start * (int64_t)c.n_cols + c.feature_cols[f]];
+      st.welford[wi + 1] = 0.0;
+    }
+  }
 }
 
-__global__ void __launch_bounds__(FX_WARPS_PER_BLOCK * 32)
-fx_observe_kernel(const __grid_constant__ FxKernelParams P, float* __restrict__ obs) {
-  extern __shared__ __align__(16) unsigned char fx_smem[];
+// writes the observation of the current state (what reset() returns): one warp per env
+__global__ void __launch_bounds__(128) fx_observe_kernel(const __grid_constant__ FxKernelParams P, float* __restrict__ obs) {
+  __shared__ double smean[4][FXENV_MAX_FEATURES], srcp[4][FXENV_MAX_FEATURES];
   const FxConfig& c = P.cfg;
+  const FxDeviceState& st = P.st;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int env = blockIdx.x * FX_WARPS_PER_BLOCK + warp;
+  const int env = blockIdx.x * 4 + warp;
   if (env >= c.num_envs) return;
-  const int ring_len = (c.reward == FX_REWARD_SHARPE) ? c.sharpe_window : 0;
-  const WarpSmem ws = fx_carve(fx_smem + (size_t)warp * P.smem_per_warp, P.cap, ring_len);
+  const FxPairTable& tb = P.pair[env % c.num_pairs];
   FxEnvRegs e;
-  fx_load_regs(P.st, env, e);
-  fx_write_obs(P, P.pair[env % c.num_pairs], lane, ws, e, P.st.total_bars[env], P.st.start[env],
-               obs + (int64_t)env * P.obs_dim);
+  e.equity = st.equity[env]; e.psize = st.psize[env]; e.price = st.price[env];
+  e.position = st.position[env]; e.bar_index = st.bar_index[env];
+  const int32_t total_bars = st.total_bars[env];
+  const int64_t start = st.start[env];
+  int s = e.bar_index;
+  if (s < 1) s = 1;
+  if (s > total_bars) s = total_bars;  // app/env.py:228
+  float* row = obs + (int64_t)env * P.obs_dim;
+  if (lane == 0) fx_write_scalars(P, tb, e, total_bars, start, row);
+  fx_stream_windows<false>(P, tb, env, lane, s, start, smean[warp], srcp[warp], row);
 }
 
 // Per-bar rolling z-score statistics (feature_window_preprocessor._scale_window :96-124 for a FULL window):
@@ -443,28 +565,49 @@ __global__ void fx_stats_kernel(FxConfig c, const double* __restrict__ candles, 
   stats[idx * 2 + 1] = rc;
 }
 
-}  // namespace
+typedef void (*StepKernel)(const FxKernelParams, const void*, float*, float*, double*, uint8_t*);
 
-size_t fx_smem_per_warp(const FxConfig& cfg, int cap) {
-  const int ring_len = (cfg.reward == FX_REWARD_SHARPE) ? cfg.sharpe_window : 0;
-  size_t b = (size_t)cap * 3 * 8 + 2 * FXENV_MAX_FEATURES * 8 + (size_t)ring_len * 8 + (size_t)cap * 4 + 8 * 4;
-  return (b + 15) & ~(size_t)15;
+template <int STRAT, int REWARD>
+StepKernel pick_fast(bool fast5) {
+  return fast5 ? fx_step_kernel<STRAT, REWARD, true> : fx_step_kernel<STRAT, REWARD, false>;
 }
 
+template <int STRAT>
+StepKernel pick_reward(int reward, bool fast5) {
+  switch (reward) {
+    case FX_REWARD_PNL: return pick_fast<STRAT, FX_REWARD_PNL>(fast5);
+    case FX_REWARD_SHARPE: return pick_fast<STRAT, FX_REWARD_SHARPE>(fast5);
+    default: return pick_fast<STRAT, FX_REWARD_DD>(fast5);
+  }
+}
+
+StepKernel pick_kernel(const FxKernelParams& P) {
+  const bool fast5 = P.fast_features == 5;
+  switch (P.cfg.strategy) {
+    case FX_STRATEGY_DEFAULT: return pick_reward<FX_STRATEGY_DEFAULT>(P.cfg.reward, fast5);
+    case FX_STRATEGY_FIXED_SLTP: return pick_reward<FX_STRATEGY_FIXED_SLTP>(P.cfg.reward, fast5);
+    default: return pick_reward<FX_STRATEGY_ATR_SLTP>(P.cfg.reward, fast5);
+  }
+}
+
+size_t step_smem_bytes(const FxKernelParams& P) {
+  const int ring_len = (P.cfg.reward == FX_REWARD_SHARPE) ? P.cfg.sharpe_window : 0;
+  return fx_warp_smem_bytes(P.cap + FXO_SLACK, ring_len) * FX_WARPS;
+}
+
+}  // namespace
+
 // dynamic shared memory above the 48 KB default needs an explicit opt-in per kernel
-cudaError_t fx_configure_kernels(size_t smem_per_block) {
-  if (smem_per_block <= 48 * 1024) return cudaSuccess;
-  cudaError_t e = cudaFuncSetAttribute(fx_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_per_block);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(fx_observe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_per_block);
+cudaError_t fx_configure_kernels(const FxKernelParams& P) {
+  const size_t smem = step_smem_bytes(P);
+  if (smem <= 48 * 1024) return cudaSuccess;
+  return cudaFuncSetAttribute(pick_kernel(P), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 
 cudaError_t fx_launch_step(const FxKernelParams& P, const void* actions, float* obs, float* reward, double* reward64,
                            uint8_t* terminated, cudaStream_t stream) {
-  const int N = P.cfg.num_envs;
-  const int blocks = (N + FX_WARPS_PER_BLOCK - 1) / FX_WARPS_PER_BLOCK;
-  const size_t smem = (size_t)P.smem_per_warp * FX_WARPS_PER_BLOCK;
-  fx_step_kernel<<<blocks, FX_WARPS_PER_BLOCK * 32, smem, stream>>>(P, actions, obs, reward, reward64, terminated);
+  const int blocks = (P.cfg.num_envs + FX_WARPS - 1) / FX_WARPS;
+  pick_kernel(P)<<<blocks, FX_WARPS * 32, step_smem_bytes(P), stream>>>(P, actions, obs, reward, reward64, terminated);
   return cudaGetLastError();
 }
 
@@ -477,9 +620,7 @@ cudaError_t fx_launch_reset(const FxKernelParams& P, const int64_t* start_bar, c
 
 cudaError_t fx_launch_observe(const FxKernelParams& P, float* obs, cudaStream_t stream) {
   const int N = P.cfg.num_envs;
-  const int blocks = (N + FX_WARPS_PER_BLOCK - 1) / FX_WARPS_PER_BLOCK;
-  const size_t smem = (size_t)P.smem_per_warp * FX_WARPS_PER_BLOCK;
-  fx_observe_kernel<<<blocks, FX_WARPS_PER_BLOCK * 32, smem, stream>>>(P, obs);
+  fx_observe_kernel<<<(N + 3) / 4, 128, 0, stream>>>(P, obs);
   return cudaGetLastError();
 }
 

@@ -17,8 +17,11 @@ struct FxPairTable {
 };
 
 // Per-env state: struct-of-arrays over N envs.  The info columns of the C-ABI (FxInfoPtrs) point straight in here.
+// Invariants at kernel boundaries: bar_index == t + 1, position == sign(psize), price == CLOSE[start + t], and the
+// broker's cached value == equity -- so the step kernel only LOADS cash/psize/pprice/equity (+ counters) and
+// re-derives the rest; prev_equity / price / position / bar_index are stored for the info columns.
 struct FxDeviceState {
-  double *cash, *psize, *pprice, *value;                  // broker: cash, position size/price, cached value
+  double *cash, *psize, *pprice;                          // broker: cash, position size / average price
   double *equity, *prev_equity, *price, *commission_paid; // bridge (app/bt_bridge.py:30-66)
   double* dd_peak;                                        // dd_penalized_reward._peak
   int64_t* start;                                         // first bar (table row) of the episode window
@@ -26,21 +29,26 @@ struct FxDeviceState {
   int32_t *sh_len, *sh_head, *sh_last_step, *dd_last_step;
   uint32_t* flags;
   double* sh_ring;   // [N][sharpe_window]
-  uint32_t* o_meta;  // [N][cap]   order table, entry-major per env (a warp scans one env's entries coalesced)
+  double* welford;   // [N][FXENV_MAX_FEATURES][2] running {mean, M2} of each feature column over rows [0, s)
+  uint32_t* o_meta;  // [N][cap + FXO_SLACK]  order table, entry-major per env (a warp scans one env coalesced)
   double *o_p0, *o_p1, *o_sz;
 };
+
+#define FX_NSTAMP 10
 
 struct FxKernelParams {
   FxConfig cfg;
   FxPairTable pair[FXENV_MAX_PAIRS];
   FxDeviceState st;
+  double inv_initial_cash;  // 1 / (initial_cash or 1.0)
+  long long* timing;        // debug (FXENV_TIMING=1): [N][FX_NSTAMP] clock64() phase stamps of the last step, else nullptr
   int32_t obs_dim;
-  int32_t cap;          // order-table capacity (multiple of 32)
-  int32_t smem_per_warp;
-  int32_t fast_features;  // 1: feature columns are 0..F-1 == all table columns (contiguous window block)
+  int32_t cap;              // logical order-table capacity (multiple of 32); arrays hold cap + FXO_SLACK
+  int32_t debug;            // timing experiments only (FXENV_DEBUG): 1 skip obs windows, 2 skip broker/strategy/reward
+  int32_t fast_features;    // 5: F == n_cols == 5 with identity columns (the [W][5] block is one contiguous span)
 };
 
-#define FX_WARPS_PER_BLOCK 4
+#define FX_WARPS 4  // warps (= envs) per CTA of the step kernel
 
 // host-callable launchers (fx_kernels.cu)
 cudaError_t fx_launch_step(const FxKernelParams& P, const void* actions, float* obs, float* reward, double* reward64,
@@ -49,5 +57,4 @@ cudaError_t fx_launch_reset(const FxKernelParams& P, const int64_t* start_bar, c
                             cudaStream_t stream);
 cudaError_t fx_launch_observe(const FxKernelParams& P, float* obs, cudaStream_t stream);
 cudaError_t fx_launch_stats(const FxConfig& cfg, const double* candles, double* stats, int64_t T, cudaStream_t stream);
-size_t fx_smem_per_warp(const FxConfig& cfg, int cap);
-cudaError_t fx_configure_kernels(size_t smem_per_block);
+cudaError_t fx_configure_kernels(const FxKernelParams& P);

@@ -26,7 +26,7 @@ HsEnv* hs_create(const FxConfig* cfg, int pair, const double* tbl, int64_t T, co
   HsEnv* h = new HsEnv();
   h->c = *cfg; h->tbl = tbl; h->T = T; h->minutes = minutes; h->pair = pair;
   int cap = cfg->order_capacity ? cfg->order_capacity : 128; cap = (cap + 31) & ~31; h->c.order_capacity = cap;
-  h->meta.assign(cap, 0); h->p0.assign(cap, 0); h->p1.assign(cap, 0); h->sz.assign(cap, 0); h->n = 0;
+  h->meta.assign(cap + FXO_SLACK, 0); h->p0.assign(cap + FXO_SLACK, 0); h->p1.assign(cap + FXO_SLACK, 0); h->sz.assign(cap + FXO_SLACK, 0); h->n = 0;
   h->ring.assign(cfg->sharpe_window > 0 ? cfg->sharpe_window : 1, 0.0);
   h->sh_len = h->sh_head = 0; h->sh_last = h->dd_last = -1; h->dd_peak = 0.0;
   return h;
@@ -59,7 +59,7 @@ void hs_step(HsEnv* h, double action_in, double* reward, uint8_t* term) {
   else { t += 1; advance = true; }
   const double* r = h->tbl + (h->start + t) * (int64_t)C;
   FxBar b{r[0], r[1], r[2], r[3]};
-  FxOrderTab tab{h->meta.data(), h->p0.data(), h->p1.data(), h->sz.data(), h->n, c.order_capacity, h->n};
+  FxOrderTab tab{h->meta.data(), h->p0.data(), h->p1.data(), h->sz.data(), h->n, c.order_capacity, h->n, 0};
   if (advance && tab.n > 0) {
     const int n = tab.n;
     std::vector<char> hit(n);
@@ -67,15 +67,10 @@ void hs_step(HsEnv* h, double action_in, double* reward, uint8_t* term) {
     for (int k = 0; k < n; k++) {
       tab.meta[k] = fx_entry_begin_bar(tab.meta[k]);
       if ((tab.meta[k] & FXO_SUBMITTED) && first_sub == n) first_sub = k;
-      hit[k] = fx_entry_hits(tab.meta[k], tab.p0[k], tab.p1[k], tab.sz[k], b);
+      hit[k] = fx_entry_hits(tab.meta[k], tab.p0[k], tab.p1[k], b);
     }
     fx_check_submitted(c, e, tab, first_sub);
     for (int k = 0; k < n; k++) if (hit[k]) fx_exec_entry(c, e, tab, k, b);
-    int w = 0;
-    for (int k = 0; k < n; k++) if (!(tab.meta[k] & FXO_DEAD)) {
-      tab.meta[w] = tab.meta[k]; tab.p0[w] = tab.p0[k]; tab.p1[w] = tab.p1[k]; tab.sz[w] = tab.sz[k]; w++;
-    }
-    tab.n = w;
   }
   if (advance) fx_mark_to_market(c, e, b.c);
   if (!exhausted) {
@@ -92,7 +87,7 @@ void hs_step(HsEnv* h, double action_in, double* reward, uint8_t* term) {
       atr = fx_neumaier_done(s_, comp) / (double)nb; ready = nb >= period;
     }
     const bool has_min = h->minutes != nullptr;
-    fx_apply_action(c, e, tab, action, b, h->pair, atr, ready, has_min, (c.session_filter && has_min) ? h->minutes[h->start + t] : 0);
+    fx_apply_action(c, c.strategy, e, tab, action, b, h->pair, atr, ready, has_min, (c.session_filter && has_min) ? h->minutes[h->start + t] : 0);
     fx_publish(e, b.c, t);
     if (e.equity <= c.min_equity) e.flags |= FX_FLAG_TERMINATED | FX_FLAG_BROKE;
   } else e.flags |= FX_FLAG_TERMINATED | FX_FLAG_EXHAUSTED;
@@ -101,8 +96,15 @@ void hs_step(HsEnv* h, double action_in, double* reward, uint8_t* term) {
   else if (c.reward == FX_REWARD_DD) rw = fx_reward_dd(c, e, h->dd_peak, h->dd_last);
   else {
     const double ret = (e.equity - e.prev_equity) / c.reward_initial_cash;
-    const int nn = fx_sharpe_push(h->ring.data(), c.sharpe_window, h->sh_len, h->sh_head, h->sh_last, e.bar_index, ret);
-    rw = fx_sharpe_eval(h->ring.data(), c.sharpe_window, nn, h->sh_head, c.annualization_factor);
+    const int nn = fx_sharpe_push(h->ring.data(), 1, c.sharpe_window, h->sh_len, h->sh_head, h->sh_last, e.bar_index, ret);
+    rw = fx_sharpe_eval(h->ring.data(), 1, c.sharpe_window, nn, h->sh_head, c.annualization_factor);
+  }
+  {  // stable compaction after the strategy call (v2 kernel phase C)
+    int w = 0;
+    for (int k = 0; k < tab.n; k++) if (!(tab.meta[k] & FXO_DEAD)) {
+      tab.meta[w] = tab.meta[k]; tab.p0[w] = tab.p0[k]; tab.p1[w] = tab.p1[k]; tab.sz[w] = tab.sz[k]; w++;
+    }
+    tab.n = w;
   }
   h->t = t; h->n = tab.n;
   *reward = rw;
@@ -115,7 +117,7 @@ void hs_scalars(HsEnv* h, float* out4) {
   const double last = h->tbl[(h->start + s - 1) * (int64_t)c.n_cols + c.price_col];
   const bool inc_price = c.preproc == FX_PREPROC_DEFAULT || c.include_price_window;
   double ref = c.preproc == FX_PREPROC_DEFAULT ? last : (inc_price ? (double)(float)last : e.price);
-  fx_agent_scalars(c, e, h->total_bars, ref, out4);
+  fx_agent_scalars(c, e, h->total_bars, ref, 1.0 / (c.initial_cash != 0.0 ? c.initial_cash : 1.0), out4);
 }
 
 void hs_info(HsEnv* h, double* d7, int32_t* i5, uint32_t* flags) {
