@@ -167,7 +167,7 @@ int fxenv_create(const FxConfig* cfg, FxEnv** out) {
     for (int i = 0; i < 5; i++) if (c.feature_cols[i] != i) env->P.fast_features = 0;
   }
   ce = fx_configure_kernels(env->P);
-  if (ce != cudaSuccess) { delete env; return cuda_fail(nullptr, ce, "order_capacity too large for shared memory"); }
+  if (ce != cudaSuccess) { delete env; return cuda_fail(nullptr, ce, "window_size * n_cols too large for shared memory"); }
   // one slab for the whole per-env state (snapshot == one memcpy)
   const size_t N = (size_t)c.num_envs;
   const size_t ring = (c.reward == FX_REWARD_SHARPE) ? (size_t)c.sharpe_window : 1;
@@ -236,7 +236,8 @@ int fxenv_load_candles(FxEnv* env, int pair_id, const double* candles_host, int6
   env->candles_dev[pair_id] = nullptr; env->stats_dev[pair_id] = nullptr; env->minutes_dev[pair_id] = nullptr;
   env->loaded[pair_id] = false;
   const size_t bytes = (size_t)T * c.n_cols * 8;
-  FX_CUDA(env, cudaMalloc(&env->candles_dev[pair_id], bytes));
+  FX_CUDA(env, cudaMalloc(&env->candles_dev[pair_id], bytes + 32));  // tail padding: TMA bulk copies are 16-B granular
+  FX_CUDA(env, cudaMemset(reinterpret_cast<char*>(env->candles_dev[pair_id]) + bytes, 0, 32));
   FX_CUDA(env, cudaMemcpy(env->candles_dev[pair_id], candles_host, bytes, cudaMemcpyHostToDevice));
   if (minutes_host) {
     FX_CUDA(env, cudaMalloc(&env->minutes_dev[pair_id], (size_t)T * 8));

@@ -4,18 +4,19 @@
 // to finish and a CTA is just FX_WARPS independent warps (no block barrier), so the ~28 warps an SM owns at 4096 envs
 // are all resident and progress concurrently.  Per warp:
 //
-//   scan     the env's order table is pulled into per-warp shared memory with ONE ORDER PER LANE (coalesced loads):
-//            bracket activation + trigger test against the new bar -> ballot hit mask; check_submitted is decided
-//            lane-parallel by a rigorous cash bound (the exact sequential simulation only runs when cash is tight);
-//   broker   the few orders that do trade are executed in FIFO order by uniform scalar fp64 code (fx_core.cuh),
-//            exactly like BackBroker.next(); then the strategy plugin's apply_action, bridge publish, reward;
-//   compact  stable lane-parallel compaction + write-back of the changed tail of the order table;
-//   observe  the observation row ([W,F] z-scored features | prices | returns | 4 agent scalars) is streamed by all
-//            lanes: coalesced fp64 reads of the L2-resident candle table, fp64 math, coalesced fp32 streaming stores.
+//   prefetch right after the state loads, lane 0 issues ONE TMA bulk copy (cp.async.bulk + mbarrier) of the env's
+//            candle window (W rows x n_cols fp64, one contiguous span of the table) into the warp's shared memory;
+//            it lands while the broker runs;
+//   broker   backtrader's per-bar pass as ONE streaming sweep over the env's order table, 32 orders (one per lane) at
+//            a time in registers: bracket activation + trigger test (ballot), the few orders that trade are executed
+//            in FIFO order by uniform scalar fp64 code (fx_core.cuh) with their fields broadcast by shuffle, then
+//            stable compaction + write-back of what changed.  check_submitted is decided lane-parallel by a rigorous
+//            cash bound (the exact sequential simulation is a cold path).  Then apply_action, publish, reward;
+//   observe  the observation row ([W,F] z-scored features | prices | returns | 4 agent scalars) is produced from the
+//            staged window: fp64 math, coalesced fp32 streaming stores (>99% of the bytes).
 //
-// Odd warps stream the observation BEFORE the broker work and even warps after it, so on every SM the bandwidth-bound
-// phase of one half overlaps the latency-bound scalar chain of the other half.  The kernel is compiled once per
-// (strategy, reward, 5-feature fast path) so each instance only carries the code its configuration can reach.
+// The kernel is compiled once per (strategy, reward, 5-feature fast path) so each instance only carries the code its
+// configuration can reach.
 // No tensor cores: there is no contraction on this path.
 //
 // Reference call stack being replaced: app/env.py:131-172 -> app/bt_bridge.py:119-150 -> strategy / reward /
@@ -28,30 +29,57 @@
 
 namespace {
 
-// per-warp shared memory: the staged order table + z-score statistics (+ the Sharpe ring)
+// per-warp shared memory: the TMA-staged candle window + z-score statistics (+ the Sharpe ring) + one mbarrier
 struct WarpSmem {
-  double *p0, *p1, *sz, *mean, *rcp, *ring;
-  uint32_t *meta, *hit;
+  double *win, *mean, *rcp, *ring;
+  unsigned long long* bar;
 };
 
-__host__ __device__ inline size_t fx_warp_smem_bytes(int capP, int ring_len) {
-  size_t b = (size_t)capP * 3 * 8 + 2 * FXENV_MAX_FEATURES * 8 + (size_t)ring_len * 8 + (size_t)capP * 4 + (size_t)(capP / 32) * 4;
+__host__ __device__ inline int fx_window_doubles(int W, int C) { return (W * C + 2 + 1) & ~1; }  // +1 alignment, even
+
+__host__ __device__ inline size_t fx_warp_smem_bytes(int win_doubles, int ring_len) {
+  size_t b = (size_t)win_doubles * 8 + 2 * FXENV_MAX_FEATURES * 8 + (size_t)ring_len * 8 + 16;
   return (b + 15) & ~(size_t)15;
 }
 
-__device__ __forceinline__ WarpSmem fx_carve(unsigned char* base, int capP, int ring_len) {
+__device__ __forceinline__ WarpSmem fx_carve(unsigned char* base, int win_doubles, int ring_len) {
   WarpSmem w;
   double* d = reinterpret_cast<double*>(base);
-  w.p0 = d; d += capP;
-  w.p1 = d; d += capP;
-  w.sz = d; d += capP;
+  w.win = d; d += win_doubles;
   w.mean = d; d += FXENV_MAX_FEATURES;
   w.rcp = d; d += FXENV_MAX_FEATURES;
   w.ring = d; d += ring_len;
-  uint32_t* u = reinterpret_cast<uint32_t*>(d);
-  w.meta = u; u += capP;
-  w.hit = u;
+  w.bar = reinterpret_cast<unsigned long long*>(d);
   return w;
+}
+
+// ---- TMA (cp.async.bulk) staging of the env's candle window: rows [left, s) of its episode, one contiguous span ----
+// Returns the element shift (0/1) needed to make the global source 16-byte aligned.  Lane 0 issues; everybody later
+// waits on the warp's mbarrier (fx_window_wait).  The table is allocated with 2 doubles of tail padding.
+__device__ __forceinline__ int fx_window_issue(const FxPairTable& tb, int C, int64_t start, int left, int have, int lane,
+                                               const WarpSmem& ws) {
+  const int64_t e0 = (start + left) * (int64_t)C;
+  const int shift = (int)(e0 & 1);
+  const unsigned bytes = (unsigned)(((have * C + shift + 1) & ~1) * 8);
+  if (lane == 0) {
+    const unsigned bar_a = (unsigned)__cvta_generic_to_shared(ws.bar);
+    const unsigned dst_a = (unsigned)__cvta_generic_to_shared(ws.win);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_a), "l"(tb.candles + (e0 - shift)), "r"(bytes), "r"(bar_a) : "memory");
+  }
+  return shift;
+}
+
+__device__ __forceinline__ void fx_window_wait(const WarpSmem& ws) {
+  __syncwarp();
+  const unsigned bar_a = (unsigned)__cvta_generic_to_shared(ws.bar);
+  unsigned ok = 0;
+  while (!ok)
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(bar_a) : "memory");
 }
 
 // GymFxEnv.reset (app/env.py:102-129): fresh bridge/broker/strategy; broker.next() on bar 0 with nothing pending
@@ -118,16 +146,17 @@ __device__ __forceinline__ bool fx_prepare_stats(const FxKernelParams& P, const 
 }
 
 // ---- observation windows: preprocessor.make_observation (features | prices | returns) in the flat VecEnv layout ----
+// `win` = the staged rows [left, s) (shift already applied): element (k, col) at win[k * C + col].
 template <bool FAST5>
-__device__ __noinline__ void fx_stream_windows(const FxKernelParams& P, const FxPairTable& tb, int env, int lane, int s,
-                                               int64_t start, double* smean, double* srcp, float* __restrict__ out) {
+__device__ __noinline__ void fx_emit_windows(const FxKernelParams& P, const FxPairTable& tb, int env, int lane, int s,
+                                                int64_t start, const double* __restrict__ win, double* smean, double* srcp,
+                                                float* __restrict__ out) {
   const FxConfig& c = P.cfg;
   const bool scale = fx_prepare_stats(P, tb, env, lane, s, start, smean, srcp);
   const int W = c.window_size, C = c.n_cols;
   int left = s - W;
   if (left < 0) left = 0;
   const int pad = W - (s - left);  // left padding with the first available row
-  const double* __restrict__ base = tb.candles + (start + left) * (int64_t)C;
   int off = 0;
   if (c.preproc == FX_PREPROC_FEATURE_WINDOW) {
     const int F = c.n_features;
@@ -135,7 +164,7 @@ __device__ __noinline__ void fx_stream_windows(const FxKernelParams& P, const Fx
     const bool do_clip = c.feature_clip > 0.0;
     const int total = W * F;
     if (FAST5 && pad == 0) {
-      // F == n_cols == 5, identity columns, full window: the [W][5] block is ONE contiguous span of the table.
+      // F == n_cols == 5, identity columns, full window: the [W][5] block is the staged span itself.
       // 30 lanes = 6 whole rows per pass, so a lane's feature (hence its mean / 1/std) is loop-invariant.
       if (lane < 30) {
         const int f = lane % 5;
@@ -143,7 +172,7 @@ __device__ __noinline__ void fx_stream_windows(const FxKernelParams& P, const Fx
         const double m = z ? smean[f] : 0.0, r = z ? srcp[f] : 1.0;
 #pragma unroll 8
         for (int j = lane; j < total; j += 30) {
-          const double x = __ldg(base + j);
+          const double x = win[j];
           const float v = z ? (float)((x - m) * r) : (float)x;
           __stcs(out + j, fx_finish(v, clipf, do_clip));
         }
@@ -155,7 +184,7 @@ __device__ __noinline__ void fx_stream_windows(const FxKernelParams& P, const Fx
       for (int j = lane; j < total; j += 32) {
         int k = w - pad;
         if (k < 0) k = 0;
-        const double x = __ldg(base + k * C + c.feature_cols[f]);
+        const double x = win[k * C + c.feature_cols[f]];
         const float v = (scale && !c.feature_binary[f]) ? (float)((x - smean[f]) * srcp[f]) : (float)x;
         __stcs(out + j, fx_finish(v, clipf, do_clip));
         w += dw; f += df;
@@ -173,12 +202,24 @@ __device__ __noinline__ void fx_stream_windows(const FxKernelParams& P, const Fx
       if (k < 0) k = 0;
       int k1 = w - 1 - pad;
       if (k1 < 0) k1 = 0;
-      const double p = __ldg(base + k * C + pc);
-      const double prev = __ldg(base + k1 * C + pc);
+      const double p = win[k * C + pc];
+      const double prev = win[k1 * C + pc];
       __stcs(out + off + w, (float)p);
       __stcs(out + off + W + w, (w == 0) ? 0.0f : (float)(p - prev));
     }
   }
+}
+
+// issue + wait + emit in one go (terminated path, observe kernel)
+template <bool FAST5>
+__device__ __forceinline__ void fx_stream_windows(const FxKernelParams& P, const FxPairTable& tb, int env, int lane, int s,
+                                                  int64_t start, const WarpSmem& ws, float* __restrict__ out) {
+  const int W = P.cfg.window_size;
+  int left = s - W;
+  if (left < 0) left = 0;
+  const int shift = fx_window_issue(tb, P.cfg.n_cols, start, left, s - left, lane, ws);
+  fx_window_wait(ws);
+  fx_emit_windows<FAST5>(P, tb, env, lane, s, start, ws.win + shift, ws.mean, ws.rcp, out);
 }
 
 __device__ __forceinline__ int fx_scalar_offset(const FxConfig& c) {
@@ -208,6 +249,17 @@ __device__ __forceinline__ void fx_write_scalars(const FxKernelParams& P, const 
 }
 
 // ---- the fused step --------------------------------------------------------------------------------------------
+#define FX_OP_KILL 1u
+#define FX_OP_ACTIVATE 2u
+#define FX_OP_ACTIVATE_NEXT 4u
+
+__device__ __forceinline__ uint32_t fx_apply_op(uint32_t m, uint32_t op) {
+  if (op & FX_OP_KILL) return m | FXO_DEAD;
+  if (op & FX_OP_ACTIVATE) return m | FXO_ACTIVE;
+  if (op & FX_OP_ACTIVATE_NEXT) return m | FXO_ACTIVATE_NEXT;
+  return m;
+}
+
 template <int STRAT, int REWARD, bool FAST5>
 __global__ void __launch_bounds__(FX_WARPS * 32, 32 / FX_WARPS)
 fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict__ actions, float* __restrict__ obs,
@@ -218,10 +270,11 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int env = blockIdx.x * FX_WARPS + warp;
   if (env >= c.num_envs) return;
-  const int capP = P.cap + FXO_SLACK;
-  const int ring_len = (REWARD == FX_REWARD_SHARPE) ? c.sharpe_window : 0;
-  const WarpSmem ws = fx_carve(fx_smem + (size_t)warp * fx_warp_smem_bytes(capP, ring_len), capP, ring_len);
   const int C = c.n_cols;
+  const int ring_len = (REWARD == FX_REWARD_SHARPE) ? c.sharpe_window : 0;
+  const int win_doubles = fx_window_doubles(c.window_size, C);
+  const WarpSmem ws = fx_carve(fx_smem + (size_t)warp * fx_warp_smem_bytes(win_doubles, ring_len), win_doubles, ring_len);
+  const int capP = P.cap + FXO_SLACK;
   const int pair = env % c.num_pairs;
   const FxPairTable& tb = P.pair[pair];
   float* __restrict__ obs_row = obs + (int64_t)env * P.obs_dim;
@@ -229,7 +282,7 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
 #define FX_STAMP(i) do { if (tstamp && lane == 0) tstamp[i] = clock64(); } while (0)
   FX_STAMP(0);
 
-  // ---- one batch of independent loads (state invariants: see FxDeviceState)
+  // ---- round trip 1: one batch of independent state loads (invariants: see FxDeviceState)
   uint32_t flags = st.flags[env];
   int32_t t = st.t[env];
   int32_t total_bars = st.total_bars[env];
@@ -241,6 +294,10 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
   e.value = e.equity;
   const double cash0 = e.cash, psize0 = e.psize, pprice0 = e.pprice, comm0 = e.commission_paid;
   const int32_t trades0 = e.trades;
+  int action_raw_i = 0;
+  float action_raw_f = 0.0f;
+  if (c.action_mode == FX_ACTION_CONTINUOUS) action_raw_f = reinterpret_cast<const float*>(actions)[env];
+  else action_raw_i = reinterpret_cast<const int32_t*>(actions)[env];
 
   // ---- terminated envs: the reference answers (obs, 0.0, True) without touching plugins (app/env.py:137-138);
   //      with auto_reset (build-side extension) the env restarts its episode window instead
@@ -269,7 +326,7 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
       terminated[env] = c.auto_reset ? 0 : 1;
       fx_write_scalars(P, tb, e, total_bars, start, obs_row);
     }
-    fx_stream_windows<FAST5>(P, tb, env, lane, e.bar_index, start, ws.mean, ws.rcp, obs_row);
+    fx_stream_windows<FAST5>(P, tb, env, lane, e.bar_index, start, ws, obs_row);
     return;
   }
 
@@ -279,6 +336,15 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
   else if (t + 1 >= total_bars) exhausted = true;  // strategy.stop(): bridge state unchanged (app/bt_bridge.py:152-155)
   else { t += 1; advance = true; }
   e.flags = flags;
+
+  // ---- round trip 2 (all issued together): TMA bulk copy of the observation window into shared memory (lands while
+  //      the broker runs), the new bar, the tail of the order table
+  const int dbg = P.debug;
+  const int s_obs = t + 1;  // bar_index after this step
+  int win_left = s_obs - c.window_size;
+  if (win_left < 0) win_left = 0;
+  int win_shift = 0;
+  if (!(dbg & 1)) win_shift = fx_window_issue(tb, C, start, win_left, s_obs - win_left, lane, ws);
 
   const double* __restrict__ row = tb.candles + (start + t) * (int64_t)C;
   FxBar b;
@@ -292,84 +358,109 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
     fx_welford_add(m, m2, row[c.feature_cols[lane]], t + 1);
     st.welford[wi] = m; st.welford[wi + 1] = m2;
   }
-  FX_STAMP(1);  // state + bar loaded, running stats updated
-
-  const int dbg = P.debug;
-  const bool obs_first = (warp & 1) != 0;
-  if (obs_first && !(dbg & 1)) fx_stream_windows<FAST5>(P, tb, env, lane, t + 1, start, ws.mean, ws.rcp, obs_row);
-  FX_STAMP(2);  // (odd warps) observation streamed
+  FX_STAMP(1);
 
   if (!(dbg & 2)) {
     const int64_t obase = (int64_t)env * capP;
-    FxOrderTab tab;
-    tab.meta = ws.meta; tab.p0 = ws.p0; tab.p1 = ws.p1; tab.sz = ws.sz;
-    tab.n = n; tab.cap = P.cap; tab.dirty_from = n; tab.ndead = 0;
+    uint32_t* __restrict__ gmeta = st.o_meta + obase;
+    double* __restrict__ gp0 = st.o_p0 + obase;
+    double* __restrict__ gp1 = st.o_p1 + obase;
+    double* __restrict__ gsz = st.o_sz + obase;
+    int n_live = n;
 
     if (advance) {
       if (n > 0) {
-        // BackBroker.next(): stage the table; activation of queued children + trigger test, one order per lane
-        int first_sub = n, first_changed = n;
-        uint32_t any_hit = 0u;
-        double need = 0.0;
-        const int nch = (n + 31) >> 5;
-        for (int ch = 0; ch < nch; ch++) {
-          const int k = ch * 32 + lane;
-          bool hit = false, sub = false, changed = false;
-          if (k < n) {
-            const uint32_t m0 = st.o_meta[obase + k];
-            const double p0 = st.o_p0[obase + k], p1 = st.o_p1[obase + k], sz = st.o_sz[obase + k];
-            const uint32_t m = fx_entry_begin_bar(m0);
-            ws.meta[k] = m; ws.p0[k] = p0; ws.p1[k] = p1; ws.sz[k] = sz;
-            changed = (m != m0);
+        // ---- check_submitted: the entries created by the previous strategy call are the last <= 3 of the table.
+        //      Lane-parallel decision by a rigorous cash bound; the exact sequential simulation (cold path, works
+        //      on the table in global memory) only runs when cash is tight.
+        int first_sub = n;
+        {
+          const int k = n - 3 + lane;
+          bool sub = false;
+          double need = 0.0;
+          if (lane < 3 && k >= 0) {
+            const uint32_t m = gmeta[k];
             sub = (m & FXO_SUBMITTED) != 0u;
-            hit = fx_entry_hits(m, p0, p1, b);
-            if (sub) need += fx_submit_cash_bound(c, m, p0, p1, sz);
+            if (sub) need = fx_submit_cash_bound(c, m, gp0[k], gp1[k], gsz[k]);
           }
-          const uint32_t hm = __ballot_sync(FX_FULL, hit);
           const uint32_t sbm = __ballot_sync(FX_FULL, sub);
-          const uint32_t cm = __ballot_sync(FX_FULL, changed);
-          if (lane == 0) ws.hit[ch] = hm;
-          any_hit |= hm;
-          if (sbm && first_sub == n) first_sub = ch * 32 + __ffs(sbm) - 1;
-          if (cm && first_changed == n) first_changed = ch * 32 + __ffs(cm) - 1;
-        }
-        __syncwarp();
-        FX_STAMP(3);  // order table staged + trigger scan done
-        tab.dirty_from = first_changed;
-        if (first_sub < n) {
-          // check_submitted: lane-parallel decision by the cash bound, exact sequential simulation only if tight
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) need += __shfl_xor_sync(FX_FULL, need, o);
-          if (e.cash >= need * 1.001) {
-            for (int k = first_sub + lane; k < n; k += 32) ws.meta[k] &= ~FXO_SUBMITTED;  // nobody can be rejected
-            if (first_sub < tab.dirty_from) tab.dirty_from = first_sub;
-            __syncwarp();
-          } else {
-            fx_check_submitted(c, e, tab, first_sub);
-          }
-        }
-        FX_STAMP(4);  // check_submitted done
-        if (any_hit) {
-          // FIFO walk over the entries that trade on this bar (uniform scalar code on the staged copy)
-          for (int ch = 0; ch < nch; ch++) {
-            uint32_t m = ws.hit[ch];
-            while (m) {
-              const int k = ch * 32 + __ffs(m) - 1;
-              m &= m - 1;
-              fx_exec_entry(c, e, tab, k, b);
+          if (sbm) {
+            first_sub = n - 3 + __ffs(sbm) - 1;
+            need += __shfl_xor_sync(FX_FULL, need, 1);
+            need += __shfl_xor_sync(FX_FULL, need, 2);
+            need = __shfl_sync(FX_FULL, need, 0);
+            if (!(e.cash >= need * 1.001)) {
+              FxOrderTab tg;
+              tg.meta = gmeta; tg.p0 = gp0; tg.p1 = gp1; tg.sz = gsz;
+              tg.n = n; tg.cap = P.cap; tg.dirty_from = n; tg.ndead = 0;
+              fx_check_submitted(c, e, tg, first_sub);  // clears SUBMITTED / marks DEAD in place
+              __syncwarp();
+              first_sub = n;                             // nothing left to accept in the pass below
             }
           }
         }
+        FX_STAMP(3);
+        // ---- BackBroker.next(): ONE streaming pass over the table, 32 entries (one per lane) at a time, in registers:
+        //      activate queued children -> trigger test (ballot) -> execute the hits in FIFO order (fields broadcast by
+        //      shuffle from the owning lane) -> stable compaction + write-back of what changed.
+        int w = 0;
+        uint32_t carry = 0u;  // operation for the first entry of the next chunk (bracket pair of a parent in lane 31)
+        for (int k0 = 0; k0 < n; k0 += 32) {
+          const int k = k0 + lane;
+          const bool valid = k < n;
+          uint32_t m0 = 0u, m = 0u;
+          double p0 = 0.0, p1 = 0.0, sz = 0.0;
+          if (valid) {
+            m0 = gmeta[k]; p0 = gp0[k]; p1 = gp1[k]; sz = gsz[k];
+            m = fx_entry_begin_bar(m0);
+            if (k >= first_sub) m &= ~FXO_SUBMITTED;  // accepted by the cash bound
+            if (lane == 0) m = fx_apply_op(m, carry);
+          }
+          carry = 0u;
+          uint32_t hm = __ballot_sync(FX_FULL, valid && !(m & FXO_DEAD) && fx_entry_hits(m, p0, p1, b));
+          while (hm) {
+            const int l = __ffs(hm) - 1;
+            hm &= hm - 1;
+            const uint32_t bm = __shfl_sync(FX_FULL, m, l);
+            if (bm & (FXO_DEAD | FXO_SUBMITTED)) continue;
+            const uint32_t kind = bm & FXO_KIND_MASK;
+            const bool buy = !(bm & FXO_SELL);
+            const double bp0 = __shfl_sync(FX_FULL, p0, l), bp1 = __shfl_sync(FX_FULL, p1, l);
+            double px = b.o;
+            bool go;
+            if (kind == FXO_MARKET) go = true;
+            else if (kind == FXO_PARENT) go = fx_match_limit(buy, bp0, b, px);
+            else go = (bm & FXO_ACTIVE) && (fx_match_stop(buy, bp0, b, px) || fx_match_limit(buy, bp1, b, px));
+            if (!go) continue;
+            // Completed or Margin: either way the entry leaves the table (a PAIR: sibling / group cancelled)
+            const bool margin = fx_execute(c, e, __shfl_sync(FX_FULL, sz, l), px);
+            if (lane == l) m |= FXO_DEAD;
+            if (kind == FXO_PARENT) {
+              const uint32_t op = margin ? FX_OP_KILL : (c.children_same_bar ? FX_OP_ACTIVATE : FX_OP_ACTIVATE_NEXT);
+              if (l < 31) { if (lane == l + 1) m = fx_apply_op(m, op); }
+              else carry = op;
+            }
+          }
+          const bool keep = valid && !(m & FXO_DEAD);
+          const uint32_t km = __ballot_sync(FX_FULL, keep);
+          if (keep) {
+            const int dst = w + __popc(km & ((1u << lane) - 1u));
+            if (dst != k) { gmeta[dst] = m; gp0[dst] = p0; gp1[dst] = p1; gsz[dst] = sz; }
+            else if (m != m0) gmeta[dst] = m;
+          }
+          w += __popc(km);
+        }
+        n_live = w;
       }
       fx_mark_to_market(c, e, b.c);
     }
-    FX_STAMP(5);  // fills executed, marked to market
+    FX_STAMP(5);  // broker pass done, marked to market
 
     double r;
+    int n_final = n_live;
     if (!exhausted) {
-      int action;
-      if (c.action_mode == FX_ACTION_CONTINUOUS) action = fx_coerce_continuous(c, reinterpret_cast<const float*>(actions)[env]);
-      else action = fx_coerce_discrete(reinterpret_cast<const int32_t*>(actions)[env]);
+      const int action = (c.action_mode == FX_ACTION_CONTINUOUS) ? fx_coerce_continuous(c, action_raw_f)
+                                                                 : fx_coerce_discrete(action_raw_i);
       double atr = 0.0;
       bool atr_ready = false;
       if (STRAT == FX_STRATEGY_ATR_SLTP && action != 0) {
@@ -397,7 +488,12 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
       }
       const bool has_min = (tb.minutes != nullptr);
       const int64_t minutes = (STRAT == FX_STRATEGY_ATR_SLTP && c.session_filter && has_min) ? tb.minutes[start + t] : 0;
-      fx_apply_action(c, STRAT, e, tab, action, b, pair, atr, atr_ready, has_min, minutes);
+      // new orders are appended straight to the (compacted) table in global memory
+      FxOrderTab tg;
+      tg.meta = gmeta; tg.p0 = gp0; tg.p1 = gp1; tg.sz = gsz;
+      tg.n = n_live; tg.cap = P.cap; tg.dirty_from = n_live; tg.ndead = 0;
+      fx_apply_action(c, STRAT, e, tg, action, b, pair, atr, atr_ready, has_min, minutes);
+      n_final = tg.n;
       fx_publish(e, b.c, t);
       if (e.equity <= c.min_equity) e.flags |= FX_FLAG_TERMINATED | FX_FLAG_BROKE;  // app/bt_bridge.py:140-143
     } else {
@@ -447,44 +543,23 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
       if (e.pprice != pprice0) st.pprice[env] = e.pprice;
       if (e.commission_paid != comm0) st.commission_paid[env] = e.commission_paid;
       if (e.trades != trades0) st.trades[env] = e.trades;
+      if (n_final != n) st.n_orders[env] = n_final;
       reward[env] = (float)r;
       if (reward64) reward64[env] = r;
       terminated[env] = term ? 1 : 0;
       fx_write_scalars(P, tb, e, total_bars, start, obs_row);
     }
-    __syncwarp();
-
-    // ---- order table: stable compaction of finished entries + write-back of the changed tail (from shared memory)
-    {
-      const int n_tot = tab.n, from = tab.dirty_from;
-      int n_live = n_tot;
-      if (from < n_tot) {
-        int w = from;
-        for (int k0 = from & ~31; k0 < n_tot; k0 += 32) {
-          const int k = k0 + lane;
-          uint32_t m = 0u;
-          bool keep = false;
-          if (k >= from && k < n_tot) { m = ws.meta[k]; keep = !(m & FXO_DEAD); }
-          const uint32_t km = __ballot_sync(FX_FULL, keep);
-          if (keep) {
-            const int dst = w + __popc(km & ((1u << lane) - 1u));
-            st.o_meta[obase + dst] = m; st.o_p0[obase + dst] = ws.p0[k]; st.o_p1[obase + dst] = ws.p1[k];
-            st.o_sz[obase + dst] = ws.sz[k];
-          }
-          w += __popc(km);
-        }
-        n_live = w;
-      }
-      if (lane == 0 && n_live != n) st.n_orders[env] = n_live;
-    }
   } else if (lane == 0) {  // timing experiment only (FXENV_DEBUG & 2): cursor only
     st.t[env] = t; st.flags[env] = flags; st.bar_index[env] = t + 1; reward[env] = 0.f; terminated[env] = 0;
   }
-  FX_STAMP(8);  // scalars written back, order table compacted
+  FX_STAMP(8);  // scalars written back
 
-  // ---- observation windows (app/env.py:160 -> preprocessor.make_observation): bar_index = t + 1
-  if (!obs_first && !(dbg & 1)) fx_stream_windows<FAST5>(P, tb, env, lane, t + 1, start, ws.mean, ws.rcp, obs_row);
-  FX_STAMP(9);  // (even warps) observation streamed
+  // ---- observation windows (app/env.py:160 -> preprocessor.make_observation) from the staged copy
+  if (!(dbg & 1)) {
+    fx_window_wait(ws);
+    fx_emit_windows<FAST5>(P, tb, env, lane, s_obs, start, ws.win + win_shift, ws.mean, ws.rcp, obs_row);
+  }
+  FX_STAMP(9);
 #undef FX_STAMP
 }
 
@@ -520,13 +595,15 @@ __global__ void fx_reset_kernel(const __grid_constant__ FxKernelParams P, const 
 }
 
 // writes the observation of the current state (what reset() returns): one warp per env
-__global__ void __launch_bounds__(128) fx_observe_kernel(const __grid_constant__ FxKernelParams P, float* __restrict__ obs) {
-  __shared__ double smean[4][FXENV_MAX_FEATURES], srcp[4][FXENV_MAX_FEATURES];
+__global__ void __launch_bounds__(FX_WARPS * 32) fx_observe_kernel(const __grid_constant__ FxKernelParams P, float* __restrict__ obs) {
+  extern __shared__ __align__(16) unsigned char fx_smem[];
   const FxConfig& c = P.cfg;
   const FxDeviceState& st = P.st;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int env = blockIdx.x * 4 + warp;
+  const int env = blockIdx.x * FX_WARPS + warp;
   if (env >= c.num_envs) return;
+  const int win_doubles = fx_window_doubles(c.window_size, c.n_cols);
+  const WarpSmem ws = fx_carve(fx_smem + (size_t)warp * fx_warp_smem_bytes(win_doubles, 0), win_doubles, 0);
   const FxPairTable& tb = P.pair[env % c.num_pairs];
   FxEnvRegs e;
   e.equity = st.equity[env]; e.psize = st.psize[env]; e.price = st.price[env];
@@ -538,7 +615,7 @@ __global__ void __launch_bounds__(128) fx_observe_kernel(const __grid_constant__
   if (s > total_bars) s = total_bars;  // app/env.py:228
   float* row = obs + (int64_t)env * P.obs_dim;
   if (lane == 0) fx_write_scalars(P, tb, e, total_bars, start, row);
-  fx_stream_windows<false>(P, tb, env, lane, s, start, smean[warp], srcp[warp], row);
+  fx_stream_windows<false>(P, tb, env, lane, s, start, ws, row);
 }
 
 // Per-bar rolling z-score statistics (feature_window_preprocessor._scale_window :96-124 for a FULL window):
@@ -592,7 +669,11 @@ StepKernel pick_kernel(const FxKernelParams& P) {
 
 size_t step_smem_bytes(const FxKernelParams& P) {
   const int ring_len = (P.cfg.reward == FX_REWARD_SHARPE) ? P.cfg.sharpe_window : 0;
-  return fx_warp_smem_bytes(P.cap + FXO_SLACK, ring_len) * FX_WARPS;
+  return fx_warp_smem_bytes(fx_window_doubles(P.cfg.window_size, P.cfg.n_cols), ring_len) * FX_WARPS;
+}
+
+size_t observe_smem_bytes(const FxKernelParams& P) {
+  return fx_warp_smem_bytes(fx_window_doubles(P.cfg.window_size, P.cfg.n_cols), 0) * FX_WARPS;
 }
 
 }  // namespace
@@ -600,8 +681,11 @@ size_t step_smem_bytes(const FxKernelParams& P) {
 // dynamic shared memory above the 48 KB default needs an explicit opt-in per kernel
 cudaError_t fx_configure_kernels(const FxKernelParams& P) {
   const size_t smem = step_smem_bytes(P);
+  if (smem > 227 * 1024) return cudaErrorInvalidValue;
   if (smem <= 48 * 1024) return cudaSuccess;
-  return cudaFuncSetAttribute(pick_kernel(P), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(pick_kernel(P), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(fx_observe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)observe_smem_bytes(P));
 }
 
 cudaError_t fx_launch_step(const FxKernelParams& P, const void* actions, float* obs, float* reward, double* reward64,
@@ -620,7 +704,7 @@ cudaError_t fx_launch_reset(const FxKernelParams& P, const int64_t* start_bar, c
 
 cudaError_t fx_launch_observe(const FxKernelParams& P, float* obs, cudaStream_t stream) {
   const int N = P.cfg.num_envs;
-  fx_observe_kernel<<<(N + 3) / 4, 128, 0, stream>>>(P, obs);
+  fx_observe_kernel<<<(N + FX_WARPS - 1) / FX_WARPS, FX_WARPS * 32, observe_smem_bytes(P), stream>>>(P, obs);
   return cudaGetLastError();
 }
 
