@@ -157,8 +157,8 @@ int fxenv_create(const FxConfig* cfg, FxEnv** out) {
   if (const char* dv = getenv("FXENV_DEBUG")) env->P.debug = atoi(dv);  // timing experiments only
   if (const char* tv = getenv("FXENV_TIMING")) {
     if (atoi(tv)) {
-      cudaMalloc(&env->P.timing, (size_t)c.num_envs * FX_NSTAMP * sizeof(long long));
-      cudaMemset(env->P.timing, 0, (size_t)c.num_envs * FX_NSTAMP * sizeof(long long));
+      cudaMalloc(&env->P.timing, (size_t)c.num_envs * 2 * FX_NSTAMP * sizeof(long long));
+      cudaMemset(env->P.timing, 0, (size_t)c.num_envs * 2 * FX_NSTAMP * sizeof(long long));
     }
   }
   env->P.fast_features = 0;
@@ -173,10 +173,10 @@ int fxenv_create(const FxConfig* cfg, FxEnv** out) {
   const size_t ring = (c.reward == FX_REWARD_SHARPE) ? (size_t)c.sharpe_window : 1;
   SlabPlan plan;
   const size_t capP = (size_t)cap + FXO_SLACK;
-  size_t o_d[8], o_start, o_i[10], o_flags, o_ring, o_welford, o_meta, o_p0, o_p1, o_sz;
-  for (int i = 0; i < 8; i++) o_d[i] = plan.add(N * 8);
+  size_t o_d[9], o_start, o_i[11], o_flags, o_ring, o_welford, o_meta, o_p0, o_p1, o_sz;
+  for (int i = 0; i < 9; i++) o_d[i] = plan.add(N * 8);
   o_start = plan.add(N * 8);
-  for (int i = 0; i < 10; i++) o_i[i] = plan.add(N * 4);
+  for (int i = 0; i < 11; i++) o_i[i] = plan.add(N * 4);
   o_flags = plan.add(N * 4);
   o_ring = plan.add(N * ring * 8);
   o_welford = plan.add(N * FXENV_MAX_FEATURES * 2 * 8);
@@ -190,13 +190,13 @@ int fxenv_create(const FxConfig* cfg, FxEnv** out) {
   cudaMemset(env->slab, 0, plan.bytes);
   FxDeviceState& st = env->P.st;
   unsigned char* b = env->slab;
-  double** dcols[8] = {&st.cash, &st.psize, &st.pprice, &st.equity, &st.prev_equity, &st.price,
-                       &st.commission_paid, &st.dd_peak};
-  for (int i = 0; i < 8; i++) *dcols[i] = reinterpret_cast<double*>(b + o_d[i]);
+  double** dcols[9] = {&st.cash, &st.psize, &st.pprice, &st.equity, &st.prev_equity, &st.price,
+                       &st.commission_paid, &st.dd_peak, &st.sub_need};
+  for (int i = 0; i < 9; i++) *dcols[i] = reinterpret_cast<double*>(b + o_d[i]);
   st.start = reinterpret_cast<int64_t*>(b + o_start);
-  int32_t** icols[10] = {&st.t, &st.total_bars, &st.position, &st.bar_index, &st.trades, &st.n_orders,
-                         &st.sh_len, &st.sh_head, &st.sh_last_step, &st.dd_last_step};
-  for (int i = 0; i < 10; i++) *icols[i] = reinterpret_cast<int32_t*>(b + o_i[i]);
+  int32_t** icols[11] = {&st.t, &st.total_bars, &st.position, &st.bar_index, &st.trades, &st.n_orders,
+                         &st.sh_len, &st.sh_head, &st.sh_last_step, &st.dd_last_step, &st.n_acc};
+  for (int i = 0; i < 11; i++) *icols[i] = reinterpret_cast<int32_t*>(b + o_i[i]);
   st.flags = reinterpret_cast<uint32_t*>(b + o_flags);
   st.sh_ring = reinterpret_cast<double*>(b + o_ring);
   st.welford = reinterpret_cast<double*>(b + o_welford);
@@ -398,12 +398,12 @@ int fxenv_set_state(FxEnv* env, const void* buf_host, int64_t nbytes) {
 
 int64_t fxenv_launch_count(const FxEnv* env) { return env ? env->launches : -1; }
 
-/* debug (FXENV_TIMING=1): copies the [num_envs][10] clock64() phase stamps of the last step; returns 10 or <0 */
+/* debug (FXENV_TIMING=1): copies the [num_envs][FX_NSTAMP] phase stamps of the last step; returns FX_NSTAMP or <0 */
 int fxenv_debug_timings(FxEnv* env, long long* out_host) {
   if (!env || !out_host || !env->P.timing) return FXENV_E_STATE;
   DeviceGuard g(env->device);
   cudaDeviceSynchronize();
-  if (cudaMemcpy(out_host, env->P.timing, (size_t)env->P.cfg.num_envs * FX_NSTAMP * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess)
+  if (cudaMemcpy(out_host, env->P.timing, (size_t)env->P.cfg.num_envs * 2 * FX_NSTAMP * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess)
     return FXENV_E_CUDA;
   return FX_NSTAMP;
 }

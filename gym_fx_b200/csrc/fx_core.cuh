@@ -72,6 +72,8 @@ struct FxOrderTab {
   int cap;         // logical capacity (live entries); the arrays hold cap + FXO_SLACK
   int dirty_from;  // smallest index whose stored copy is stale (n => nothing to write back)
   int ndead;       // entries marked FXO_DEAD since the last compaction
+  double sub_need; // sum of fx_submit_cash_bound over the entries pushed by this strategy call (set by fx_push)
+  double bound_per; // max(1, 1/leverage) + |commission|, the per-unit-notional factor of that bound
 };
 
 #define FXO_SLACK 32  // physical head-room: new orders are appended before the dead ones are compacted away
@@ -126,7 +128,7 @@ FX_HD void fx_pseudo_execute(const FxConfig& c, double size, double price, doubl
 
 // ---- BackBroker._execute, real form.  Returns true if the order ended in Margin (=> cancel its bracket group) --
 FX_HD bool fx_execute(const FxConfig& c, FxEnvRegs& e, double size, double price) {
-  const double pprice_orig = e.pprice;
+  const double pprice_orig = e.pprice, oldsize = e.psize;
   double ps = e.psize, pp = e.pprice, opened, closed;
   fx_pos_update(ps, pp, size, price, opened, closed);  // pseudoupdate on a clone
   const double pnl = (-closed) * (price - pprice_orig) * 1.0;
@@ -153,11 +155,11 @@ FX_HD bool fx_execute(const FxConfig& c, FxEnvRegs& e, double size, double price
     if (cash < 0.0) { opened = 0.0; openedcomm = 0.0; }
     else e.cash = cash;
   }
+  const bool margin = (popened != 0.0 && opened == 0.0);
   const double execsize = closed + opened;
   if (execsize != 0.0) {
-    const double oldsize = e.psize;
-    double o2, c2;
-    fx_pos_update(e.psize, e.pprice, execsize, price, o2, c2);
+    if (execsize == size) { e.psize = ps; e.pprice = pp; }  // position.update(execsize) is then exactly the clone's update
+    else { double o2, c2; fx_pos_update(e.psize, e.pprice, execsize, price, o2, c2); }
     // Trade bookkeeping (strategy._addnotification): a trade closes when the closing part of the execution
     // brings the position to exactly 0 -> BTBridgeStrategy.notify_trade (app/bt_bridge.py:115-117)
     if (closed != 0.0 && oldsize + closed == 0.0) e.trades += 1;
@@ -168,7 +170,7 @@ FX_HD bool fx_execute(const FxConfig& c, FxEnvRegs& e, double size, double price
       e.commission_paid += ocomm;
     }
   }
-  return (popened != 0.0 && opened == 0.0);
+  return margin;
 }
 
 // ---- matching rules (bbroker.py _try_exec_market / _try_exec_limit / _try_exec_stop), no slippage --------------
@@ -243,8 +245,10 @@ FX_HD_COLD void fx_check_submitted(const FxConfig& c, const FxEnvRegs& e, FxOrde
 // long; the other two cases ADD cash).  A PAIR is two pseudo-executions (stop child @p0, limit child @p1).
 // If cash >= 1.001 * (sum of the bounds of all submitted entries) no order can be rejected, and the exact sequential
 // simulation can be skipped without changing any outcome (the simulation only decides accept / reject).
+FX_HD double fx_bound_per(const FxConfig& c) { return (c.leverage < 1.0 ? 1.0 / c.leverage : 1.0) + fabs(c.commission); }
+
 FX_HD double fx_submit_cash_bound(const FxConfig& c, uint32_t meta, double p0, double p1, double sz) {
-  const double per = (c.leverage < 1.0 ? 1.0 / c.leverage : 1.0) + fabs(c.commission);
+  const double per = fx_bound_per(c);
   double need = fabs(sz) * fabs(p0) * per;
   if ((meta & FXO_KIND_MASK) == FXO_PAIR) need += fabs(sz) * fabs(p1) * per;
   return need;
@@ -290,6 +294,8 @@ FX_HD bool fx_room(FxOrderTab& t, int need, uint32_t& flags) {
 }
 
 FX_HD void fx_push(FxOrderTab& t, uint32_t meta, double p0, double p1, double sz) {
+  t.sub_need += fabs(sz) * fabs(p0) * t.bound_per;
+  if ((meta & FXO_KIND_MASK) == FXO_PAIR) t.sub_need += fabs(sz) * fabs(p1) * t.bound_per;
   const int k = t.n++;
   t.meta[k] = meta | (sz < 0.0 ? FXO_SELL : 0u); t.p0[k] = p0; t.p1[k] = p1; t.sz[k] = sz;
   if (k < t.dirty_from) t.dirty_from = k;

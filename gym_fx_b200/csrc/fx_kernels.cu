@@ -54,8 +54,17 @@ __device__ __forceinline__ WarpSmem fx_carve(unsigned char* base, int win_double
 }
 
 // ---- TMA (cp.async.bulk) staging of the env's candle window: rows [left, s) of its episode, one contiguous span ----
-// Returns the element shift (0/1) needed to make the global source 16-byte aligned.  Lane 0 issues; everybody later
-// waits on the warp's mbarrier (fx_window_wait).  The table is allocated with 2 doubles of tail padding.
+// fx_window_init (lane 0, at kernel top so that the init fence overlaps the state loads) arms the warp's mbarrier;
+// fx_window_issue starts the bulk copy and returns the element shift (0/1) that makes the global source 16-byte
+// aligned; fx_window_wait blocks until the bytes have landed.  The table is allocated with 32 B of tail padding.
+__device__ __forceinline__ void fx_window_init(int lane, const WarpSmem& ws) {
+  if (lane == 0) {
+    const unsigned bar_a = (unsigned)__cvta_generic_to_shared(ws.bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+}
+
 __device__ __forceinline__ int fx_window_issue(const FxPairTable& tb, int C, int64_t start, int left, int have, int lane,
                                                const WarpSmem& ws) {
   const int64_t e0 = (start + left) * (int64_t)C;
@@ -64,8 +73,6 @@ __device__ __forceinline__ int fx_window_issue(const FxPairTable& tb, int C, int
   if (lane == 0) {
     const unsigned bar_a = (unsigned)__cvta_generic_to_shared(ws.bar);
     const unsigned dst_a = (unsigned)__cvta_generic_to_shared(ws.win);
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst_a), "l"(tb.candles + (e0 - shift)), "r"(bytes), "r"(bar_a) : "memory");
@@ -117,27 +124,40 @@ __device__ __forceinline__ float fx_finish(float v, float clipf, bool do_clip) {
   return isinf(v) ? (v > 0.0f ? clipf : -clipf) : v;
 }
 
-// z-score statistics of the history window ending at local row s-1 -> smem mean/rcp (lanes f < F), warp-synchronous.
-// Full rolling window: the per-bar table computed at load time.  Otherwise (warm-up, expanding): running Welford state.
+// z-score statistics of the history window ending at local row s-1, for lane f < F: {mean, 1/std}.
+// Full rolling window: the per-bar table computed at load time.  Otherwise (warm-up, expanding): the env's running
+// Welford state (wm, wm2 = the lane's feature, already including row s-1).  Returns false -> raw (unscaled) values.
+__device__ __forceinline__ bool fx_scaling_active(const FxConfig& c, int s, int& hn) {
+  if (!fx_uses_running_stats(c)) return false;
+  hn = s;
+  if (c.scaling == FX_SCALING_ROLLING && hn > c.scaling_window) hn = c.scaling_window;
+  return hn >= 2;
+}
+
+__device__ __forceinline__ bool fx_stats_from_table(const FxConfig& c, const FxPairTable& tb, int hn) {
+  return c.scaling == FX_SCALING_ROLLING && hn == c.scaling_window && tb.stats != nullptr;
+}
+
+__device__ __forceinline__ void fx_welford_to_stats(double wm, double wm2, int hn, double& m, double& r) {
+  double sd = sqrt(wm2 / (double)hn);
+  if (sd < 1e-8) sd = 1.0;
+  m = wm; r = 1.0 / sd;
+}
+
+// self-contained version for the paths that are not latency critical (terminated envs, observe kernel)
 __device__ __forceinline__ bool fx_prepare_stats(const FxKernelParams& P, const FxPairTable& tb, int env, int lane, int s,
                                                  int64_t start, double* smean, double* srcp) {
   const FxConfig& c = P.cfg;
-  if (!fx_uses_running_stats(c)) return false;
-  const int F = c.n_features;
-  int hn = s;
-  if (c.scaling == FX_SCALING_ROLLING && hn > c.scaling_window) hn = c.scaling_window;
-  if (hn < 2) return false;
-  if (lane < F) {
+  int hn;
+  if (!fx_scaling_active(c, s, hn)) return false;
+  if (lane < c.n_features) {
     double m, r;
-    if (c.scaling == FX_SCALING_ROLLING && hn == c.scaling_window && tb.stats != nullptr) {
-      const double* sp = tb.stats + ((start + s - 1) * (int64_t)F + lane) * 2;
+    if (fx_stats_from_table(c, tb, hn)) {
+      const double* sp = tb.stats + ((start + s - 1) * (int64_t)c.n_features + lane) * 2;
       m = sp[0]; r = sp[1];
     } else {
       const int64_t wi = ((int64_t)env * FXENV_MAX_FEATURES + lane) * 2;
-      m = P.st.welford[wi];
-      double sd = sqrt(P.st.welford[wi + 1] / (double)hn);
-      if (sd < 1e-8) sd = 1.0;
-      r = 1.0 / sd;
+      fx_welford_to_stats(P.st.welford[wi], P.st.welford[wi + 1], hn, m, r);
     }
     smean[lane] = m; srcp[lane] = r;
   }
@@ -148,11 +168,10 @@ __device__ __forceinline__ bool fx_prepare_stats(const FxKernelParams& P, const 
 // ---- observation windows: preprocessor.make_observation (features | prices | returns) in the flat VecEnv layout ----
 // `win` = the staged rows [left, s) (shift already applied): element (k, col) at win[k * C + col].
 template <bool FAST5>
-__device__ __noinline__ void fx_emit_windows(const FxKernelParams& P, const FxPairTable& tb, int env, int lane, int s,
-                                                int64_t start, const double* __restrict__ win, double* smean, double* srcp,
-                                                float* __restrict__ out) {
+__device__ __noinline__ void fx_emit_windows(const FxKernelParams& P, int lane, int s, bool scale,
+                                             const double* __restrict__ win, const double* smean, const double* srcp,
+                                             float* __restrict__ out) {
   const FxConfig& c = P.cfg;
-  const bool scale = fx_prepare_stats(P, tb, env, lane, s, start, smean, srcp);
   const int W = c.window_size, C = c.n_cols;
   int left = s - W;
   if (left < 0) left = 0;
@@ -217,9 +236,12 @@ __device__ __forceinline__ void fx_stream_windows(const FxKernelParams& P, const
   const int W = P.cfg.window_size;
   int left = s - W;
   if (left < 0) left = 0;
+  fx_window_init(lane, ws);
+  __syncwarp();
   const int shift = fx_window_issue(tb, P.cfg.n_cols, start, left, s - left, lane, ws);
+  const bool scale = fx_prepare_stats(P, tb, env, lane, s, start, ws.mean, ws.rcp);
   fx_window_wait(ws);
-  fx_emit_windows<FAST5>(P, tb, env, lane, s, start, ws.win + shift, ws.mean, ws.rcp, out);
+  fx_emit_windows<FAST5>(P, lane, s, scale, ws.win + shift, ws.mean, ws.rcp, out);
 }
 
 __device__ __forceinline__ int fx_scalar_offset(const FxConfig& c) {
@@ -229,16 +251,13 @@ __device__ __forceinline__ int fx_scalar_offset(const FxConfig& c) {
 }
 
 // the 4 agent scalars at the end of the row (one lane)
-__device__ __forceinline__ void fx_write_scalars(const FxKernelParams& P, const FxPairTable& tb, const FxEnvRegs& e,
-                                                 int32_t total_bars, int64_t start, float* __restrict__ out) {
+// `last` = price_column of the last window row (local row bar_index - 1)
+__device__ __forceinline__ void fx_write_scalars(const FxKernelParams& P, const FxEnvRegs& e, int32_t total_bars,
+                                                 double last, float* __restrict__ out) {
   const FxConfig& c = P.cfg;
   const bool inc_agent = (c.preproc == FX_PREPROC_DEFAULT) || c.include_agent_state;
   if (!inc_agent) return;
   const bool inc_price = (c.preproc == FX_PREPROC_DEFAULT) || c.include_price_window;
-  int s = e.bar_index;
-  if (s < 1) s = 1;
-  if (s > total_bars) s = total_bars;
-  const double last = tb.candles[(start + s - 1) * (int64_t)c.n_cols + c.price_col];
   double ref;
   if (c.preproc == FX_PREPROC_DEFAULT) ref = last;       // default_preprocessor.py:63
   else ref = inc_price ? (double)(float)last : e.price;  // feature_window_preprocessor.py:218-222
@@ -274,13 +293,18 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
   const int ring_len = (REWARD == FX_REWARD_SHARPE) ? c.sharpe_window : 0;
   const int win_doubles = fx_window_doubles(c.window_size, C);
   const WarpSmem ws = fx_carve(fx_smem + (size_t)warp * fx_warp_smem_bytes(win_doubles, ring_len), win_doubles, ring_len);
+  fx_window_init(lane, ws);  // mbarrier init + fence now, so that its latency hides behind the state loads
   const int capP = P.cap + FXO_SLACK;
   const int pair = env % c.num_pairs;
   const FxPairTable& tb = P.pair[pair];
   float* __restrict__ obs_row = obs + (int64_t)env * P.obs_dim;
   long long* tstamp = P.timing ? P.timing + (int64_t)env * FX_NSTAMP : nullptr;
 #define FX_STAMP(i) do { if (tstamp && lane == 0) tstamp[i] = clock64(); } while (0)
+  // stamp taken only after `dep` (a loaded value) has actually arrived in a register
+#define FX_STAMP_DEP(i, dep) do { if (tstamp) { long long t__; unsigned long long d__ = (unsigned long long)(dep); \
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t__) : "l"(d__)); if (lane == 0) tstamp[i] = t__; } } while (0)
   FX_STAMP(0);
+  if (tstamp && lane == 0) { long long g__; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g__)); tstamp[10] = g__; }
 
   // ---- round trip 1: one batch of independent state loads (invariants: see FxDeviceState)
   uint32_t flags = st.flags[env];
@@ -288,6 +312,8 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
   int32_t total_bars = st.total_bars[env];
   const int64_t start = st.start[env];
   const int n = st.n_orders[env];
+  const int n_acc = st.n_acc[env];
+  const double sub_need = st.sub_need[env];
   FxEnvRegs e;
   e.cash = st.cash[env]; e.psize = st.psize[env]; e.pprice = st.pprice[env]; e.equity = st.equity[env];
   e.commission_paid = st.commission_paid[env]; e.trades = st.trades[env];
@@ -298,6 +324,13 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
   float action_raw_f = 0.0f;
   if (c.action_mode == FX_ACTION_CONTINUOUS) action_raw_f = reinterpret_cast<const float*>(actions)[env];
   else action_raw_i = reinterpret_cast<const int32_t*>(actions)[env];
+
+  if (tstamp) {  // keep two consecutive steps: slot = parity of the (pre-step) cursor
+    long long* nb = P.timing + ((int64_t)(t & 1) * c.num_envs + env) * FX_NSTAMP;
+    if (lane == 0) { nb[0] = tstamp[0]; nb[10] = tstamp[10]; }
+    tstamp = nb;
+  }
+  FX_STAMP_DEP(2, (unsigned long long)flags + (unsigned long long)t + (unsigned long long)start + (unsigned long long)total_bars);
 
   // ---- terminated envs: the reference answers (obs, 0.0, True) without touching plugins (app/env.py:137-138);
   //      with auto_reset (build-side extension) the env restarts its episode window instead
@@ -312,7 +345,7 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
       }
       if (lane == 0) {
         fx_store_all(st, env, e);
-        st.t[env] = 0; st.total_bars[env] = total_bars; st.n_orders[env] = 0;
+        st.t[env] = 0; st.total_bars[env] = total_bars; st.n_orders[env] = 0; st.n_acc[env] = 0; st.sub_need[env] = 0.0;
       }
     } else {
       e.flags = flags;
@@ -324,9 +357,18 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
       reward[env] = 0.0f;
       if (reward64) reward64[env] = 0.0;
       terminated[env] = c.auto_reset ? 0 : 1;
-      fx_write_scalars(P, tb, e, total_bars, start, obs_row);
+      fx_write_scalars(P, e, total_bars, tb.candles[(start + e.bar_index - 1) * (int64_t)C + c.price_col], obs_row);
     }
-    fx_stream_windows<FAST5>(P, tb, env, lane, e.bar_index, start, ws, obs_row);
+    {
+      const int s = e.bar_index;
+      int left = s - c.window_size;
+      if (left < 0) left = 0;
+      __syncwarp();
+      const int shift = fx_window_issue(tb, C, start, left, s - left, lane, ws);
+      const bool scale = fx_prepare_stats(P, tb, env, lane, s, start, ws.mean, ws.rcp);
+      fx_window_wait(ws);
+      fx_emit_windows<FAST5>(P, lane, s, scale, ws.win + shift, ws.mean, ws.rcp, obs_row);
+    }
     return;
   }
 
@@ -337,67 +379,82 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
   else { t += 1; advance = true; }
   e.flags = flags;
 
-  // ---- round trip 2 (all issued together): TMA bulk copy of the observation window into shared memory (lands while
-  //      the broker runs), the new bar, the tail of the order table
+  // ---- round trip 2: everything that only needs the cursor is requested together -- the new bar, the z-score
+  //      statistics, the first 32 orders of the table, and the TMA bulk copy of the observation window (which lands
+  //      in shared memory while the broker runs)
   const int dbg = P.debug;
   const int s_obs = t + 1;  // bar_index after this step
-  int win_left = s_obs - c.window_size;
-  if (win_left < 0) win_left = 0;
-  int win_shift = 0;
-  if (!(dbg & 1)) win_shift = fx_window_issue(tb, C, start, win_left, s_obs - win_left, lane, ws);
+  const int64_t obase = (int64_t)env * capP;
+  uint32_t* __restrict__ gmeta = st.o_meta + obase;
+  double* __restrict__ gp0 = st.o_p0 + obase;
+  double* __restrict__ gp1 = st.o_p1 + obase;
+  double* __restrict__ gsz = st.o_sz + obase;
 
   const double* __restrict__ row = tb.candles + (start + t) * (int64_t)C;
   FxBar b;
   b.o = row[0]; b.h = row[1]; b.l = row[2]; b.c = row[3];
+  const double last_price = row[c.price_col];
 
-  // running z-score statistics while the history window is still growing (or expanding_zscore)
-  if (advance && fx_uses_running_stats(c) && (c.scaling == FX_SCALING_EXPANDING || t + 1 <= c.scaling_window) &&
-      lane < c.n_features) {
-    const int64_t wi = ((int64_t)env * FXENV_MAX_FEATURES + lane) * 2;
-    double m = st.welford[wi], m2 = st.welford[wi + 1];
-    fx_welford_add(m, m2, row[c.feature_cols[lane]], t + 1);
-    st.welford[wi] = m; st.welford[wi + 1] = m2;
+  int hn = 0;
+  const bool scale = fx_scaling_active(c, s_obs, hn);
+  const bool table_stats = scale && fx_stats_from_table(c, tb, hn);
+  const bool welford_live = advance && fx_uses_running_stats(c) && (c.scaling == FX_SCALING_EXPANDING || t + 1 <= c.scaling_window);
+  double st_m = 0.0, st_r = 1.0, wf_m = 0.0, wf_m2 = 0.0, wf_x = 0.0;
+  if (lane < c.n_features) {
+    if (table_stats) {
+      const double* sp = tb.stats + ((start + t) * (int64_t)c.n_features + lane) * 2;
+      st_m = sp[0]; st_r = sp[1];
+    }
+    if (welford_live || (scale && !table_stats)) {
+      const int64_t wi = ((int64_t)env * FXENV_MAX_FEATURES + lane) * 2;
+      wf_m = st.welford[wi]; wf_m2 = st.welford[wi + 1];
+      if (welford_live) wf_x = row[c.feature_cols[lane]];
+    }
   }
-  FX_STAMP(1);
+  // first chunk of the order table (one order per lane)
+  uint32_t pm0 = 0u;
+  double pp0 = 0.0, pp1 = 0.0, psz = 0.0;
+  if (advance && lane < n && !(dbg & 2)) { pm0 = gmeta[lane]; pp0 = gp0[lane]; pp1 = gp1[lane]; psz = gsz[lane]; }
+
+  int win_left = s_obs - c.window_size;
+  if (win_left < 0) win_left = 0;
+  int win_shift = 0;
+  __syncwarp();
+  if (!(dbg & 1)) win_shift = fx_window_issue(tb, C, start, win_left, s_obs - win_left, lane, ws);
+  FX_STAMP(4);  // round trip 2 issued
+
+  // running z-score statistics while the history window is still growing (or expanding_zscore); stats -> smem
+  if (lane < c.n_features) {
+    if (welford_live) {
+      fx_welford_add(wf_m, wf_m2, wf_x, t + 1);
+      const int64_t wi = ((int64_t)env * FXENV_MAX_FEATURES + lane) * 2;
+      st.welford[wi] = wf_m; st.welford[wi + 1] = wf_m2;
+    }
+    if (scale) {
+      if (!table_stats) fx_welford_to_stats(wf_m, wf_m2, hn, st_m, st_r);
+      ws.mean[lane] = st_m; ws.rcp[lane] = st_r;
+    }
+  }
+  FX_STAMP_DEP(1, __double_as_longlong(b.o) + __double_as_longlong(b.c));  // the new bar has arrived
 
   if (!(dbg & 2)) {
-    const int64_t obase = (int64_t)env * capP;
-    uint32_t* __restrict__ gmeta = st.o_meta + obase;
-    double* __restrict__ gp0 = st.o_p0 + obase;
-    double* __restrict__ gp1 = st.o_p1 + obase;
-    double* __restrict__ gsz = st.o_sz + obase;
     int n_live = n;
 
     if (advance) {
       if (n > 0) {
-        // ---- check_submitted: the entries created by the previous strategy call are the last <= 3 of the table.
-        //      Lane-parallel decision by a rigorous cash bound; the exact sequential simulation (cold path, works
-        //      on the table in global memory) only runs when cash is tight.
-        int first_sub = n;
-        {
-          const int k = n - 3 + lane;
-          bool sub = false;
-          double need = 0.0;
-          if (lane < 3 && k >= 0) {
-            const uint32_t m = gmeta[k];
-            sub = (m & FXO_SUBMITTED) != 0u;
-            if (sub) need = fx_submit_cash_bound(c, m, gp0[k], gp1[k], gsz[k]);
-          }
-          const uint32_t sbm = __ballot_sync(FX_FULL, sub);
-          if (sbm) {
-            first_sub = n - 3 + __ffs(sbm) - 1;
-            need += __shfl_xor_sync(FX_FULL, need, 1);
-            need += __shfl_xor_sync(FX_FULL, need, 2);
-            need = __shfl_sync(FX_FULL, need, 0);
-            if (!(e.cash >= need * 1.001)) {
-              FxOrderTab tg;
-              tg.meta = gmeta; tg.p0 = gp0; tg.p1 = gp1; tg.sz = gsz;
-              tg.n = n; tg.cap = P.cap; tg.dirty_from = n; tg.ndead = 0;
-              fx_check_submitted(c, e, tg, first_sub);  // clears SUBMITTED / marks DEAD in place
-              __syncwarp();
-              first_sub = n;                             // nothing left to accept in the pass below
-            }
-          }
+        // ---- check_submitted: the entries created by the previous strategy call are [n_acc, n); their cash bound
+        //      was stored when they were created.  If cash covers it nobody can be rejected; otherwise the exact
+        //      sequential simulation (cold path) runs on the table in global memory.
+        int first_sub = n_acc;
+        bool reload0 = false;
+        if (n_acc < n && !(e.cash >= sub_need * 1.001)) {
+          FxOrderTab tg;
+          tg.meta = gmeta; tg.p0 = gp0; tg.p1 = gp1; tg.sz = gsz;
+          tg.n = n; tg.cap = P.cap; tg.dirty_from = n; tg.ndead = 0; tg.sub_need = 0.0; tg.bound_per = 0.0;
+          fx_check_submitted(c, e, tg, first_sub);  // clears SUBMITTED / marks DEAD in place
+          __syncwarp();
+          first_sub = n;    // nothing left to accept in the pass below
+          reload0 = true;   // the prefetched chunk may be stale
         }
         FX_STAMP(3);
         // ---- BackBroker.next(): ONE streaming pass over the table, 32 entries (one per lane) at a time, in registers:
@@ -411,7 +468,8 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
           uint32_t m0 = 0u, m = 0u;
           double p0 = 0.0, p1 = 0.0, sz = 0.0;
           if (valid) {
-            m0 = gmeta[k]; p0 = gp0[k]; p1 = gp1[k]; sz = gsz[k];
+            if (k0 == 0 && !reload0) { m0 = pm0; p0 = pp0; p1 = pp1; sz = psz; }
+            else { m0 = gmeta[k]; p0 = gp0[k]; p1 = gp1[k]; sz = gsz[k]; }
             m = fx_entry_begin_bar(m0);
             if (k >= first_sub) m &= ~FXO_SUBMITTED;  // accepted by the cash bound
             if (lane == 0) m = fx_apply_op(m, carry);
@@ -457,7 +515,8 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
     FX_STAMP(5);  // broker pass done, marked to market
 
     double r;
-    int n_final = n_live;
+    int n_final = n_live, n_acc_new = n_live;
+    double sub_need_new = 0.0;
     if (!exhausted) {
       const int action = (c.action_mode == FX_ACTION_CONTINUOUS) ? fx_coerce_continuous(c, action_raw_f)
                                                                  : fx_coerce_discrete(action_raw_i);
@@ -488,12 +547,14 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
       }
       const bool has_min = (tb.minutes != nullptr);
       const int64_t minutes = (STRAT == FX_STRATEGY_ATR_SLTP && c.session_filter && has_min) ? tb.minutes[start + t] : 0;
-      // new orders are appended straight to the (compacted) table in global memory
+      // new orders are appended straight to the (compacted) table in global memory; their check_submitted cash
+      // bound is accumulated by fx_push and kept in the env state for the next step
       FxOrderTab tg;
       tg.meta = gmeta; tg.p0 = gp0; tg.p1 = gp1; tg.sz = gsz;
-      tg.n = n_live; tg.cap = P.cap; tg.dirty_from = n_live; tg.ndead = 0;
+      tg.n = n_live; tg.cap = P.cap; tg.dirty_from = n_live; tg.ndead = 0; tg.sub_need = 0.0; tg.bound_per = fx_bound_per(c);
       fx_apply_action(c, STRAT, e, tg, action, b, pair, atr, atr_ready, has_min, minutes);
       n_final = tg.n;
+      sub_need_new = tg.sub_need;
       fx_publish(e, b.c, t);
       if (e.equity <= c.min_equity) e.flags |= FX_FLAG_TERMINATED | FX_FLAG_BROKE;  // app/bt_bridge.py:140-143
     } else {
@@ -502,6 +563,7 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
       e.bar_index = t + 1;
       e.position = e.psize > 0.0 ? 1 : (e.psize < 0.0 ? -1 : 0);
       e.price = b.c;
+      n_acc_new = n_acc; sub_need_new = sub_need;  // nothing was processed
     }
     FX_STAMP(6);  // strategy + publish
 
@@ -544,10 +606,12 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
       if (e.commission_paid != comm0) st.commission_paid[env] = e.commission_paid;
       if (e.trades != trades0) st.trades[env] = e.trades;
       if (n_final != n) st.n_orders[env] = n_final;
+      if (n_acc_new != n_acc) st.n_acc[env] = n_acc_new;
+      if (sub_need_new != sub_need) st.sub_need[env] = sub_need_new;
       reward[env] = (float)r;
       if (reward64) reward64[env] = r;
       terminated[env] = term ? 1 : 0;
-      fx_write_scalars(P, tb, e, total_bars, start, obs_row);
+      fx_write_scalars(P, e, total_bars, last_price, obs_row);
     }
   } else if (lane == 0) {  // timing experiment only (FXENV_DEBUG & 2): cursor only
     st.t[env] = t; st.flags[env] = flags; st.bar_index[env] = t + 1; reward[env] = 0.f; terminated[env] = 0;
@@ -557,10 +621,12 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
   // ---- observation windows (app/env.py:160 -> preprocessor.make_observation) from the staged copy
   if (!(dbg & 1)) {
     fx_window_wait(ws);
-    fx_emit_windows<FAST5>(P, tb, env, lane, s_obs, start, ws.win + win_shift, ws.mean, ws.rcp, obs_row);
+    fx_emit_windows<FAST5>(P, lane, s_obs, scale, ws.win + win_shift, ws.mean, ws.rcp, obs_row);
   }
   FX_STAMP(9);
+  if (tstamp && lane == 0) { long long g__; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g__)); tstamp[11] = g__; }
 #undef FX_STAMP
+#undef FX_STAMP_DEP
 }
 
 __global__ void fx_reset_kernel(const __grid_constant__ FxKernelParams P, const int64_t* __restrict__ start_bar,
@@ -585,6 +651,8 @@ __global__ void fx_reset_kernel(const __grid_constant__ FxKernelParams P, const 
   st.t[env] = 0;
   st.total_bars[env] = fx_total_bars(c, tb.T, start);
   st.n_orders[env] = 0;
+  st.n_acc[env] = 0;
+  st.sub_need[env] = 0.0;
   if (fx_uses_running_stats(c)) {
     for (int f = 0; f < c.n_features; f++) {
       const int64_t wi = ((int64_t)env * FXENV_MAX_FEATURES + f) * 2;
@@ -614,7 +682,7 @@ __global__ void __launch_bounds__(FX_WARPS * 32) fx_observe_kernel(const __grid_
   if (s < 1) s = 1;
   if (s > total_bars) s = total_bars;  // app/env.py:228
   float* row = obs + (int64_t)env * P.obs_dim;
-  if (lane == 0) fx_write_scalars(P, tb, e, total_bars, start, row);
+  if (lane == 0) fx_write_scalars(P, e, total_bars, tb.candles[(start + s - 1) * (int64_t)c.n_cols + c.price_col], row);
   fx_stream_windows<false>(P, tb, env, lane, s, start, ws, row);
 }
 

@@ -24,8 +24,9 @@ struct FxDeviceState {
   double *cash, *psize, *pprice;                          // broker: cash, position size / average price
   double *equity, *prev_equity, *price, *commission_paid; // bridge (app/bt_bridge.py:30-66)
   double* dd_peak;                                        // dd_penalized_reward._peak
+  double* sub_need;                                       // check_submitted cash bound of the entries [n_acc, n_orders)
   int64_t* start;                                         // first bar (table row) of the episode window
-  int32_t *t, *total_bars, *position, *bar_index, *trades, *n_orders;
+  int32_t *t, *total_bars, *position, *bar_index, *trades, *n_orders, *n_acc;
   int32_t *sh_len, *sh_head, *sh_last_step, *dd_last_step;
   uint32_t* flags;
   double* sh_ring;   // [N][sharpe_window]
@@ -34,7 +35,7 @@ struct FxDeviceState {
   double *o_p0, *o_p1, *o_sz;
 };
 
-#define FX_NSTAMP 10
+#define FX_NSTAMP 12
 
 struct FxKernelParams {
   FxConfig cfg;

@@ -59,7 +59,7 @@ void hs_step(HsEnv* h, double action_in, double* reward, uint8_t* term) {
   else { t += 1; advance = true; }
   const double* r = h->tbl + (h->start + t) * (int64_t)C;
   FxBar b{r[0], r[1], r[2], r[3]};
-  FxOrderTab tab{h->meta.data(), h->p0.data(), h->p1.data(), h->sz.data(), h->n, c.order_capacity, h->n, 0};
+  FxOrderTab tab{h->meta.data(), h->p0.data(), h->p1.data(), h->sz.data(), h->n, c.order_capacity, h->n, 0, 0.0, fx_bound_per(c)};
   if (advance && tab.n > 0) {
     const int n = tab.n;
     std::vector<char> hit(n);

@@ -22,18 +22,30 @@ for _ in range(5):
     env.step_many(acts, ring, rews, terms)
 torch.cuda.synchronize()
 env.L.fxenv_debug_timings.argtypes = [C.c_void_p, C.c_void_p]
-buf = np.zeros((N, 10), np.int64)
-assert env.L.fxenv_debug_timings(env._h, buf.ctypes.data) == 10
-names = ["loads+stats", "obs(odd warps)", "stage+scan", "check_submitted", "fills+mtm", "strategy+publish", "reward", "writeback+compact", "obs(even warps)"]
+buf2 = np.zeros((2, N, 12), np.int64)
+assert env.L.fxenv_debug_timings(env._h, buf2.ctypes.data) == 12
+lastslot = int(np.argmax([buf2[0,:,10].max(), buf2[1,:,10].max()]))
+buf = buf2[lastslot]; prev = buf2[1 - lastslot]
 t = buf.astype(np.float64)
 clk = 1.965  # GHz (clocks.max.sm)
-print(f"{desc}\nper-warp phase durations of the LAST step (cycles @~{clk} GHz -> us), mean / p50 / p95 / max over {N} warps")
-for i, nm in enumerate(names):
-    a, b = t[:, i], t[:, i + 1]
-    if i == 2: a = t[:, 2]; b = np.where(t[:, 3] > 0, t[:, 3], t[:, 2])
-    d = b - a
-    d = d[(a > 0) & (b > 0)]
-    if d.size == 0: print(f"  {nm:20s} n/a"); continue
-    print(f"  {nm:20s} {d.mean():9.0f} cyc {d.mean()/clk/1e3:6.2f} us | p50 {np.median(d):8.0f} p95 {np.percentile(d,95):8.0f} max {d.max():8.0f}  (n={d.size})")
-tot = t[:, 9] - t[:, 0]
-print(f"  {'TOTAL warp lifetime':20s} {tot.mean():9.0f} cyc {tot.mean()/clk/1e3:6.2f} us | p50 {np.median(tot):8.0f} p95 {np.percentile(tot,95):8.0f} max {tot.max():8.0f}")
+segs = [("start -> state arrived", 0, 2), ("state -> TMA issued", 2, 4), ("TMA issued -> bar arrived", 4, 1),
+        ("bar -> check_submitted done", 1, 3), ("order pass + mark-to-market", 3, 5), ("strategy + publish", 5, 6),
+        ("reward", 6, 7), ("write-back", 7, 8), ("wait window + emit obs", 8, 9), ("TOTAL warp lifetime", 0, 9)]
+print(f"{desc}\nper-warp phase durations of the LAST step (cycles @~{clk} GHz -> us), over {N} warps")
+for nm, a, b in segs:
+    x, y = t[:, a], t[:, b]
+    ok = (x > 0) & (y > 0)
+    d = (y - x)[ok]
+    if d.size == 0:
+        print(f"  {nm:32s} n/a"); continue
+    print(f"  {nm:32s} {d.mean():9.0f} cyc {d.mean()/clk/1e3:6.2f} us | p50 {np.median(d):8.0f} p95 {np.percentile(d,95):8.0f} max {d.max():8.0f}  (n={d.size})")
+g0, g1 = buf[:, 10].astype(np.float64), buf[:, 11].astype(np.float64)
+base = g0.min()
+print(f"  globaltimer (ns): first warp start 0, last warp start {g0.max()-base:.0f}, p50 start {np.median(g0)-base:.0f}, p95 start {np.percentile(g0,95)-base:.0f}; "
+      f"last warp end {g1.max()-base:.0f}; warp lifetime mean {(g1-g0).mean():.0f} max {(g1-g0).max():.0f}")
+order = np.argsort(g0)
+print("  start time (ns) of every 128th warp by start order:", [int(g0[order[i]]-base) for i in range(0, N, max(1, N//32))])
+print("  env ids of the 8 last-starting warps:", order[-8:].tolist(), " and 8 first:", order[:8].tolist())
+pg0, pg1 = prev[:, 10].astype(np.float64), prev[:, 11].astype(np.float64)
+print(f"  consecutive steps: prev kernel first start {pg0.min()-base:.0f} ns, prev last end {pg1.max()-base:.0f} ns -> period {g0.min()-pg0.min():.0f} ns, "
+      f"gap (prev last warp end -> this first warp start) {g0.min()-pg1.max():.0f} ns, active span {g1.max()-g0.min():.0f} ns")
