@@ -61,7 +61,7 @@ __device__ __forceinline__ void fx_window_init(int lane, const WarpSmem& ws) {
   if (lane == 0) {
     const unsigned bar_a = (unsigned)__cvta_generic_to_shared(ws.bar);
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // CTA-scope: the cluster-scope init fence costs an L1 invalidate (CCTL.IVALL)
   }
 }
 
@@ -117,13 +117,6 @@ __device__ __forceinline__ bool fx_uses_running_stats(const FxConfig& c) {
   return c.preproc == FX_PREPROC_FEATURE_WINDOW && c.scaling != FX_SCALING_NONE;
 }
 
-// np.clip (float32) + np.nan_to_num(nan=0, posinf=clip, neginf=-clip), feature_window_preprocessor.py:119-123
-__device__ __forceinline__ float fx_finish(float v, float clipf, bool do_clip) {
-  v = (v != v) ? 0.0f : v;
-  if (do_clip) return fminf(fmaxf(v, -clipf), clipf);  // also maps +-inf to +-clip
-  return isinf(v) ? (v > 0.0f ? clipf : -clipf) : v;
-}
-
 // z-score statistics of the history window ending at local row s-1, for lane f < F: {mean, 1/std}.
 // Full rolling window: the per-bar table computed at load time.  Otherwise (warm-up, expanding): the env's running
 // Welford state (wm, wm2 = the lane's feature, already including row s-1).  Returns false -> raw (unscaled) values.
@@ -167,10 +160,18 @@ __device__ __forceinline__ bool fx_prepare_stats(const FxKernelParams& P, const 
 
 // ---- observation windows: preprocessor.make_observation (features | prices | returns) in the flat VecEnv layout ----
 // `win` = the staged rows [left, s) (shift already applied): element (k, col) at win[k * C + col].
-template <bool FAST5>
-__device__ __noinline__ void fx_emit_windows(const FxKernelParams& P, int lane, int s, bool scale,
-                                             const double* __restrict__ win, const double* smean, const double* srcp,
-                                             float* __restrict__ out) {
+// float32 finishing of one feature value: np.clip then np.nan_to_num (feature_window_preprocessor.py:119-123)
+template <bool CLIP>
+__device__ __forceinline__ float fx_finish_t(float v, float clipf) {
+  v = (v != v) ? 0.0f : v;
+  if (CLIP) return fminf(fmaxf(v, -clipf), clipf);  // also maps +-inf to +-clip
+  return isinf(v) ? (v > 0.0f ? clipf : -clipf) : v;
+}
+
+template <bool FAST5, bool CLIP>
+__device__ __noinline__ void fx_emit_windows_t(const FxKernelParams& P, int lane, int s, bool scale,
+                                               const double* __restrict__ win, const double* smean, const double* srcp,
+                                               float* __restrict__ out) {
   const FxConfig& c = P.cfg;
   const int W = c.window_size, C = c.n_cols;
   int left = s - W;
@@ -180,20 +181,30 @@ __device__ __noinline__ void fx_emit_windows(const FxKernelParams& P, int lane, 
   if (c.preproc == FX_PREPROC_FEATURE_WINDOW) {
     const int F = c.n_features;
     const float clipf = (float)c.feature_clip;
-    const bool do_clip = c.feature_clip > 0.0;
     const int total = W * F;
-    if (FAST5 && pad == 0) {
-      // F == n_cols == 5, identity columns, full window: the [W][5] block is the staged span itself.
-      // 30 lanes = 6 whole rows per pass, so a lane's feature (hence its mean / 1/std) is loop-invariant.
+    if (FAST5 && pad == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0) {  // row must be 8-byte aligned for float2
+      // F == n_cols == 5, identity columns, full window: the [W][5] block is the staged span itself.  A lane owns the
+      // element PAIR (2*lane, 2*lane+1) of every 60-element (12-row) pass: its two features -- hence their mean and
+      // 1/std -- are loop-invariant, and each pass ends in one 8-byte streaming store per lane (30 lanes active).
       if (lane < 30) {
-        const int f = lane % 5;
-        const bool z = scale && !c.feature_binary[f];
-        const double m = z ? smean[f] : 0.0, r = z ? srcp[f] : 1.0;
-#pragma unroll 8
-        for (int j = lane; j < total; j += 30) {
+        const int f0 = (2 * lane) % 5, f1 = (2 * lane + 1) % 5;
+        const bool z0 = scale && !c.feature_binary[f0], z1 = scale && !c.feature_binary[f1];
+        const double m0 = z0 ? smean[f0] : 0.0, r0 = z0 ? srcp[f0] : 1.0;
+        const double m1 = z1 ? smean[f1] : 0.0, r1 = z1 ? srcp[f1] : 1.0;
+        const int npair = total >> 1;  // total = 5 W; an odd W leaves one tail element
+#pragma unroll 4
+        for (int q = lane; q < npair; q += 30) {
+          const double x0 = win[2 * q], x1 = win[2 * q + 1];
+          float2 v;
+          v.x = fx_finish_t<CLIP>((float)((x0 - m0) * r0), clipf);
+          v.y = fx_finish_t<CLIP>((float)((x1 - m1) * r1), clipf);
+          __stcs(reinterpret_cast<float2*>(out) + q, v);
+        }
+        if ((total & 1) && lane == 0) {
+          const int j = total - 1, f = j % 5;
+          const bool z = scale && !c.feature_binary[f];
           const double x = win[j];
-          const float v = z ? (float)((x - m) * r) : (float)x;
-          __stcs(out + j, fx_finish(v, clipf, do_clip));
+          __stcs(out + j, fx_finish_t<CLIP>(z ? (float)((x - smean[f]) * srcp[f]) : (float)x, clipf));
         }
       }
     } else {
@@ -205,7 +216,7 @@ __device__ __noinline__ void fx_emit_windows(const FxKernelParams& P, int lane, 
         if (k < 0) k = 0;
         const double x = win[k * C + c.feature_cols[f]];
         const float v = (scale && !c.feature_binary[f]) ? (float)((x - smean[f]) * srcp[f]) : (float)x;
-        __stcs(out + j, fx_finish(v, clipf, do_clip));
+        __stcs(out + j, fx_finish_t<CLIP>(v, clipf));
         w += dw; f += df;
         if (f >= F) { f -= F; w += 1; }
       }
@@ -215,6 +226,7 @@ __device__ __noinline__ void fx_emit_windows(const FxKernelParams& P, int lane, 
   const bool inc_price = (c.preproc == FX_PREPROC_DEFAULT) || c.include_price_window;
   if (inc_price) {
     const int pc = c.price_col;
+    float* __restrict__ op = out + off;
 #pragma unroll 4
     for (int w = lane; w < W; w += 32) {
       int k = w - pad;
@@ -223,10 +235,18 @@ __device__ __noinline__ void fx_emit_windows(const FxKernelParams& P, int lane, 
       if (k1 < 0) k1 = 0;
       const double p = win[k * C + pc];
       const double prev = win[k1 * C + pc];
-      __stcs(out + off + w, (float)p);
-      __stcs(out + off + W + w, (w == 0) ? 0.0f : (float)(p - prev));
+      __stcs(op + w, (float)p);
+      __stcs(op + W + w, (w == 0) ? 0.0f : (float)(p - prev));
     }
   }
+}
+
+template <bool FAST5>
+__device__ __forceinline__ void fx_emit_windows(const FxKernelParams& P, int lane, int s, bool scale,
+                                                const double* __restrict__ win, const double* smean, const double* srcp,
+                                                float* __restrict__ out) {
+  if (P.cfg.feature_clip > 0.0) fx_emit_windows_t<FAST5, true>(P, lane, s, scale, win, smean, srcp, out);
+  else fx_emit_windows_t<FAST5, false>(P, lane, s, scale, win, smean, srcp, out);
 }
 
 // issue + wait + emit in one go (terminated path, observe kernel)
@@ -295,16 +315,23 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
   const WarpSmem ws = fx_carve(fx_smem + (size_t)warp * fx_warp_smem_bytes(win_doubles, ring_len), win_doubles, ring_len);
   fx_window_init(lane, ws);  // mbarrier init + fence now, so that its latency hides behind the state loads
   const int capP = P.cap + FXO_SLACK;
-  const int pair = env % c.num_pairs;
+  const int pair = (c.num_pairs == 1) ? 0 : env % c.num_pairs;
   const FxPairTable& tb = P.pair[pair];
   float* __restrict__ obs_row = obs + (int64_t)env * P.obs_dim;
+#ifdef FXENV_ENABLE_TIMING  // phase instrumentation build (make TIMING=1): tools/phase_timing.py
   long long* tstamp = P.timing ? P.timing + (int64_t)env * FX_NSTAMP : nullptr;
 #define FX_STAMP(i) do { if (tstamp && lane == 0) tstamp[i] = clock64(); } while (0)
   // stamp taken only after `dep` (a loaded value) has actually arrived in a register
 #define FX_STAMP_DEP(i, dep) do { if (tstamp) { long long t__; unsigned long long d__ = (unsigned long long)(dep); \
     asm volatile("mov.u64 %0, %%clock64;" : "=l"(t__) : "l"(d__)); if (lane == 0) tstamp[i] = t__; } } while (0)
+#define FX_STAMP_GLOBAL(i) do { if (tstamp && lane == 0) { long long g__; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g__)); tstamp[i] = g__; } } while (0)
+#else
+#define FX_STAMP(i) do { } while (0)
+#define FX_STAMP_DEP(i, dep) do { } while (0)
+#define FX_STAMP_GLOBAL(i) do { } while (0)
+#endif
   FX_STAMP(0);
-  if (tstamp && lane == 0) { long long g__; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g__)); tstamp[10] = g__; }
+  FX_STAMP_GLOBAL(10);
 
   // ---- round trip 1: one batch of independent state loads (invariants: see FxDeviceState)
   uint32_t flags = st.flags[env];
@@ -325,11 +352,13 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
   if (c.action_mode == FX_ACTION_CONTINUOUS) action_raw_f = reinterpret_cast<const float*>(actions)[env];
   else action_raw_i = reinterpret_cast<const int32_t*>(actions)[env];
 
+#ifdef FXENV_ENABLE_TIMING
   if (tstamp) {  // keep two consecutive steps: slot = parity of the (pre-step) cursor
     long long* nb = P.timing + ((int64_t)(t & 1) * c.num_envs + env) * FX_NSTAMP;
     if (lane == 0) { nb[0] = tstamp[0]; nb[10] = tstamp[10]; }
     tstamp = nb;
   }
+#endif
   FX_STAMP_DEP(2, (unsigned long long)flags + (unsigned long long)t + (unsigned long long)start + (unsigned long long)total_bars);
 
   // ---- terminated envs: the reference answers (obs, 0.0, True) without touching plugins (app/env.py:137-138);
@@ -421,7 +450,6 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
   int win_shift = 0;
   __syncwarp();
   if (!(dbg & 1)) win_shift = fx_window_issue(tb, C, start, win_left, s_obs - win_left, lane, ws);
-  FX_STAMP(4);  // round trip 2 issued
 
   // running z-score statistics while the history window is still growing (or expanding_zscore); stats -> smem
   if (lane < c.n_features) {
@@ -461,6 +489,9 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
         //      activate queued children -> trigger test (ballot) -> execute the hits in FIFO order (fields broadcast by
         //      shuffle from the owning lane) -> stable compaction + write-back of what changed.
         int w = 0;
+#ifdef FXENV_ENABLE_TIMING
+        int n_fills = 0;
+#endif
         uint32_t carry = 0u;  // operation for the first entry of the next chunk (bracket pair of a parent in lane 31)
         for (int k0 = 0; k0 < n; k0 += 32) {
           const int k = k0 + lane;
@@ -492,6 +523,9 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
             if (!go) continue;
             // Completed or Margin: either way the entry leaves the table (a PAIR: sibling / group cancelled)
             const bool margin = fx_execute(c, e, __shfl_sync(FX_FULL, sz, l), px);
+#ifdef FXENV_ENABLE_TIMING
+            n_fills++;
+#endif
             if (lane == l) m |= FXO_DEAD;
             if (kind == FXO_PARENT) {
               const uint32_t op = margin ? FX_OP_KILL : (c.children_same_bar ? FX_OP_ACTIVATE : FX_OP_ACTIVATE_NEXT);
@@ -509,6 +543,9 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
           w += __popc(km);
         }
         n_live = w;
+#ifdef FXENV_ENABLE_TIMING
+        if (tstamp && lane == 0) tstamp[4] = ((long long)n << 32) | (long long)n_fills;  // debug: table size, fills
+#endif
       }
       fx_mark_to_market(c, e, b.c);
     }
@@ -624,9 +661,10 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
     fx_emit_windows<FAST5>(P, lane, s_obs, scale, ws.win + win_shift, ws.mean, ws.rcp, obs_row);
   }
   FX_STAMP(9);
-  if (tstamp && lane == 0) { long long g__; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g__)); tstamp[11] = g__; }
+  FX_STAMP_GLOBAL(11);
 #undef FX_STAMP
 #undef FX_STAMP_DEP
+#undef FX_STAMP_GLOBAL
 }
 
 __global__ void fx_reset_kernel(const __grid_constant__ FxKernelParams P, const int64_t* __restrict__ start_bar,

@@ -28,7 +28,7 @@ lastslot = int(np.argmax([buf2[0,:,10].max(), buf2[1,:,10].max()]))
 buf = buf2[lastslot]; prev = buf2[1 - lastslot]
 t = buf.astype(np.float64)
 clk = 1.965  # GHz (clocks.max.sm)
-segs = [("start -> state arrived", 0, 2), ("state -> TMA issued", 2, 4), ("TMA issued -> bar arrived", 4, 1),
+segs = [("start -> state arrived", 0, 2), ("state -> bar arrived", 2, 1),
         ("bar -> check_submitted done", 1, 3), ("order pass + mark-to-market", 3, 5), ("strategy + publish", 5, 6),
         ("reward", 6, 7), ("write-back", 7, 8), ("wait window + emit obs", 8, 9), ("TOTAL warp lifetime", 0, 9)]
 print(f"{desc}\nper-warp phase durations of the LAST step (cycles @~{clk} GHz -> us), over {N} warps")
@@ -49,3 +49,11 @@ print("  env ids of the 8 last-starting warps:", order[-8:].tolist(), " and 8 fi
 pg0, pg1 = prev[:, 10].astype(np.float64), prev[:, 11].astype(np.float64)
 print(f"  consecutive steps: prev kernel first start {pg0.min()-base:.0f} ns, prev last end {pg1.max()-base:.0f} ns -> period {g0.min()-pg0.min():.0f} ns, "
       f"gap (prev last warp end -> this first warp start) {g0.min()-pg1.max():.0f} ns, active span {g1.max()-g0.min():.0f} ns")
+
+tot = (t[:, 9] - t[:, 0]) / clk / 1e3
+nf = (buf[:, 4] & 0xffffffff).astype(np.int64); ntab = (buf[:, 4] >> 32).astype(np.int64)
+print("  warp lifetime us percentiles: p50 %.1f p90 %.1f p99 %.1f p99.9 %.1f max %.1f" % tuple(np.percentile(tot, [50, 90, 99, 99.9, 100])))
+print("  fills per env-step: mean %.2f p50 %d p90 %d p99 %d max %d ; table entries: mean %.1f p99 %d max %d" % (nf.mean(), *np.percentile(nf, [50, 90, 99, 100]).astype(int), ntab.mean(), *np.percentile(ntab, [99, 100]).astype(int)))
+for lo, hi in ((0, 0), (1, 1), (2, 3), (4, 7), (8, 15), (16, 1000)):
+    sel = (nf >= lo) & (nf <= hi)
+    if sel.any(): print(f"    fills {lo}-{hi}: {sel.sum():5d} warps, lifetime mean {tot[sel].mean():6.2f} us max {tot[sel].max():6.2f}")
