@@ -56,6 +56,7 @@ def build_workload(name, envs_override=None):
     from gym_fx_b200.synth import PAIR_PIP, synth_candles, synth_minutes
 
     envs, W, strat, rew, pairs, R = WORKLOADS[name]
+    W = int(os.environ.get("FXENV_BENCH_WINDOW", W))  # experiments only
     if envs_override:
         envs = envs_override
     cfgd = {**DEFAULTS, "window_size": W, "feature_columns": list(OHLCV)}

@@ -12,7 +12,7 @@ import subprocess
 from .config import FxConfig
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfxenv.so")
+LIB_PATH = os.path.join(_HERE, os.environ.get("FXENV_LIB", "libfxenv.so"))  # FXENV_LIB: experiment builds
 CSRC = os.path.join(_HERE, "csrc")
 
 EXPORTS = [

@@ -300,7 +300,7 @@ __device__ __forceinline__ uint32_t fx_apply_op(uint32_t m, uint32_t op) {
 }
 
 template <int STRAT, int REWARD, bool FAST5>
-__global__ void __launch_bounds__(FX_WARPS * 32, 32 / FX_WARPS)
+__global__ void __launch_bounds__(FX_WARPS * 32, FX_MIN_BLOCKS)
 fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict__ actions, float* __restrict__ obs,
                float* __restrict__ reward, double* __restrict__ reward64, uint8_t* __restrict__ terminated) {
   extern __shared__ __align__(16) unsigned char fx_smem[];

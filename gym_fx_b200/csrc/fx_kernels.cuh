@@ -50,6 +50,12 @@ struct FxKernelParams {
 };
 
 #define FX_WARPS 4  // warps (= envs) per CTA of the step kernel
+// CTAs per SM the step kernel is compiled for.  Measured on B200 (cfg2, us/step at 4096 / 16384 envs):
+//   8 (64 regs, 220 B of spills) 30.4 / 73.1 | 6: 29.8 / 71.1 | 5: 28.1 / 69.8 | 4 (128 regs, no spills) 26.2 / 65.0 |
+//   3: 28.7 / 75.9.  The spill-free build wins although 4096 envs then run as two waves of 16 warps per SM.
+#ifndef FX_MIN_BLOCKS
+#define FX_MIN_BLOCKS 4
+#endif
 
 // host-callable launchers (fx_kernels.cu)
 cudaError_t fx_launch_step(const FxKernelParams& P, const void* actions, float* obs, float* reward, double* reward64,

@@ -13,15 +13,6 @@ tests) timeout 900 python -m pytest tests -m gpu -q -p no:cacheprovider --timeou
 bench) for wl in cfg2 cfg3 cfg4 cfg5; do
          timeout 300 python bench.py --workload $wl --steps 1000 --warmup 100 > $OUT/bench_$wl.json 2> $OUT/bench_$wl.err; echo "bench $wl rc=$?"; tail -c 1500 $OUT/bench_$wl.json; done
        timeout 300 python bench.py --impl reference --steps 200 --warmup 5 > $OUT/bench_ref.json 2> $OUT/bench_ref.err; tail -c 600 $OUT/bench_ref.json ;;
-tune)  for wl in cfg2 cfg3; do for tile in 4 8 16 32; do
-         FXENV_TILE=$tile timeout 200 python bench.py --workload $wl --steps 1000 --warmup 300 --no-cpu-baseline > $OUT/tune_${wl}_t$tile.json 2>$OUT/tune.err
-         python - <<PY
-import json
-try:
-    d=json.load(open("$OUT/tune_${wl}_t$tile.json")); print("$wl tile $tile: %.1f M steps/s, %.2f us/step, frac %.3f, e2e %.1f M" % (d["value"]/1e6, d["ms_per_step"]*1e3, d["roofline"]["frac"], d["e2e"]["value"]/1e6))
-except Exception as ex: print("$wl tile $tile failed", ex)
-PY
-       done; done ;;
 ncu)   timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 320 -c 100 --csv --log-file $OUT/launches.csv \
          python bench.py --steps 100 --warmup 300 --no-cpu-baseline > $OUT/ncu_launch.log 2>&1; echo "ncu launches rc=$?"
        timeout 600 ncu --set full --clock-control none --import-source on -k regex:fx_step -s 340 -c 2 -f -o $OUT/prof_step \

@@ -2,6 +2,7 @@
 """Debug: per-phase clock64() durations of the step kernel in a steady-state CUDA-graph run (FXENV_TIMING=1)."""
 import ctypes as C, os, sys
 os.environ["FXENV_TIMING"] = "1"
+os.environ.setdefault("FXENV_LIB", "libfxenv_timing.so")  # built by `make -C gym_fx_b200/csrc timing`
 sys.path[:0] = [os.path.dirname(os.path.dirname(os.path.abspath(__file__)))]
 import numpy as np, torch
 import bench
