@@ -47,7 +47,7 @@ WORKLOADS = {
 }
 T_BARS = 1 << 19
 L2_BYTES = 126 * 1024 * 1024
-ORDER_CAP = int(os.environ.get("FXENV_ORDER_CAP", "128"))  # order-table entries per env (overflowing envs are reported)
+ORDER_CAP = int(os.environ.get("FXENV_ORDER_CAP", "256"))  # order-table entries per env (overflowing envs are reported)
 
 
 def build_workload(name, envs_override=None):
@@ -121,25 +121,27 @@ def measured_peak_gbs():
 
 
 def cpu_port_rate(workload, total_envs, steps, warmup, threads, budget_s=None):
-    """env-steps/s of the oracle port on the host.  Each step = one lockstep tick of `total_envs` envs."""
+    """env-steps/s of the oracle port on the host: every env stepped `steps` times by `threads` host threads, each
+    thread running its env slice through the steps without a per-step barrier (envs are independent)."""
     from gym_fx_b200.synth import start_offsets
     from oracle.c_oracle import OracleVec, ParallelStepper
-    import ctypes as C
 
     cfg, candles, minutes, envs, D, _, desc = build_workload(workload, total_envs)
     vec = OracleVec(cfg, candles, minutes)
-    vec.reset(start_offsets(total_envs, T_BARS, steps + warmup, 256))
+    vec.reset(start_offsets(total_envs, T_BARS, steps + warmup + 64, 256))
     ps = ParallelStepper(vec, threads)
     rng = np.random.default_rng(1234)
-    acts = rng.integers(0, 3, (64, total_envs)).astype(np.int32)
-    for k in range(warmup):
-        ps.step(acts[k % 64])
+    chunk = 8
+    acts = rng.integers(0, 3, (chunk, total_envs)).astype(np.int32)
+    if warmup:
+        ps.run(acts[:min(warmup, chunk)])
     t0 = time.perf_counter()
     done = 0
-    for k in range(steps):
-        ps.step(acts[k % 64])
-        done += 1
-        if budget_s is not None and time.perf_counter() - t0 > budget_s and done >= 5:
+    while done < steps:
+        k = min(chunk, steps - done)
+        ps.run(acts[:k])
+        done += k
+        if budget_s is not None and time.perf_counter() - t0 > budget_s:
             break
     dt = time.perf_counter() - t0
     vec.close()
@@ -162,7 +164,7 @@ def run_reference(args, rank, world):
                    "note": "CPU arm: C port of the reference path (oracle/fxenv_oracle.c); the Python reference "
                            "(~1.3-1.5k steps/s/process per SURVEY section 6) cannot travel to the GPU box"},
         "cpu_baseline": {"value": rate, "unit": "env-steps/s", "cores": used, "kind": "port",
-                         "sample": f"{total} envs x {done} lockstep steps, all {used} host threads (pthreads)"},
+                         "sample": f"{total} envs x {done} steps, {used} host threads (pthreads), each thread runs its env slice without a per-step barrier"},
         "e2e": {"value": rate, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -171,7 +173,7 @@ def run_reference(args, rank, world):
 
 def run_ours(args, rank, world, local_rank):
     import torch
-    from gym_fx_b200.synth import start_offsets
+    from gym_fx_b200.sharding import check_pair_alignment, shard_starts
     from gym_fx_b200.vec_env import VecFxEnv
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device for --impl ours"
@@ -186,7 +188,8 @@ def run_ours(args, rank, world, local_rank):
     K, Wm = args.steps, max(3, args.warmup)
     env = VecFxEnv(cfg, candles, minutes, device=dev)
     # envs are sharded by rank: global env id = rank * N + i (no collective in the data path)
-    starts = torch.as_tensor(start_offsets(N * world, T_BARS, K + Wm + 64, 256)[rank * N:(rank + 1) * N])
+    check_pair_alignment(N, cfg.num_pairs)
+    starts = torch.as_tensor(shard_starts(N, rank, world, T_BARS, K + Wm + 64, 256))
     env.reset(starts)
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
@@ -287,8 +290,8 @@ def run_ours(args, rank, world, local_rank):
             sample_envs = min(N, 4096)
             rate, done, dt, used, _ = cpu_port_rate(args.workload, sample_envs, 100000, 3, threads, budget_s=8.0)
             line["cpu_baseline"] = {"value": rate, "unit": "env-steps/s", "cores": used, "kind": "port",
-                                    "sample": f"{sample_envs} envs x {done} lockstep steps ({dt:.1f} s), C oracle port, "
-                                              f"{used} host threads"}
+                                    "sample": f"{sample_envs} envs x {done} steps ({dt:.1f} s), C oracle port, {used} host threads, "
+                                              f"no per-step barrier"}
         print(json.dumps(line), flush=True)
     env.close()
     if dist:

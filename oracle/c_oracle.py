@@ -58,6 +58,8 @@ def lib():
         L.fxo_step_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                      C.c_void_p, C.c_void_p, C.c_void_p]
         L.fxo_step_batch_mt.argtypes = L.fxo_step_batch.argtypes + [C.c_int]
+        L.fxo_run_mt.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                 C.c_void_p, C.c_void_p, C.c_int]
         assert L.fxo_config_size() == C.sizeof(FxConfig), "FxConfig layout mismatch (python vs C)"
         assert L.fxo_info_size() == C.sizeof(FxoInfo)
         _lib = L
@@ -163,6 +165,15 @@ class ParallelStepper:
         v.L.fxo_step_batch_mt(v._arr, v.N, None if is_f else actions.ctypes.data, actions.ctypes.data if is_f else None,
                               self.obs.ctypes.data, v.D, self.rew.ctypes.data, None, self.term.ctypes.data,
                               self.threads)
+        return self.obs, self.rew, self.term
+
+    def run(self, actions: np.ndarray):
+        """K = actions.shape[0] steps of every env, no per-step barrier between threads (throughput baseline)."""
+        v = self.vec
+        is_f = v.cfg.action_mode == 1
+        a = np.ascontiguousarray(actions, np.float32 if is_f else np.int32)
+        v.L.fxo_run_mt(v._arr, v.N, a.shape[0], None if is_f else a.ctypes.data, a.ctypes.data if is_f else None,
+                       self.obs.ctypes.data, v.D, self.rew.ctypes.data, self.term.ctypes.data, self.threads)
         return self.obs, self.rew, self.term
 
     def close(self):
