@@ -287,6 +287,56 @@ __device__ __forceinline__ void fx_write_scalars(const FxKernelParams& P, const 
   o[0] = sc[0]; o[1] = sc[1]; o[2] = sc[2]; o[3] = sc[3];
 }
 
+// ---- Sharpe: lane-parallel evaluation of the deque statistics -----------------------------------------------------
+// The reference sums the <= window returns with Python's compensated sum() (sequential Neumaier).  Here every lane
+// accumulates its share as an error-free (hi, lo) pair (Knuth two-sum; the build uses -fmad=false so each operation
+// rounds once) and the pairs are merged across the warp: the total is accurate to ~1e-32 relative before the final
+// rounding, i.e. it can differ from the reference's result only where Neumaier itself is not correctly rounded
+// (<= 1 ulp; the reward tolerance is 1e-9 in fp64, 1e-5 in fp32).  All-equal and all-zero windows stay exact, so the
+// `std <= 0 -> 0.0` rule fires exactly when the reference's does (flat episodes).
+__device__ __forceinline__ void fx_two_sum(double a, double b, double& s, double& e) {
+  s = a + b;
+  const double bb = s - a;
+  e = (a - (s - bb)) + (b - bb);
+}
+
+__device__ __forceinline__ void fx_dd_add(double& hi, double& lo, double x) {
+  double s, e;
+  fx_two_sum(hi, x, s, e);
+  lo += e;
+  hi = s;
+}
+
+__device__ __forceinline__ double fx_dd_warp_total(double hi, double lo) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double h2 = __shfl_xor_sync(FX_FULL, hi, o), l2 = __shfl_xor_sync(FX_FULL, lo, o);
+    double s, e;
+    fx_two_sum(hi, h2, s, e);
+    e += lo + l2;
+    hi = s + e;           // fast two-sum renormalisation
+    lo = e - (hi - s);
+  }
+  return hi + lo;
+}
+
+__device__ __forceinline__ double fx_sharpe_eval_warp(const double* ring, int W, int n, int head, double ann, int lane) {
+  if (n < 2) return 0.0;
+  double hi = 0.0, lo = 0.0;
+  for (int i = lane; i < n; i += 32) { int idx = head + i; if (idx >= W) idx -= W; fx_dd_add(hi, lo, ring[idx]); }
+  const double mean = fx_dd_warp_total(hi, lo) / (double)n;
+  hi = 0.0; lo = 0.0;
+  for (int i = lane; i < n; i += 32) {
+    int idx = head + i; if (idx >= W) idx -= W;
+    const double d = ring[idx] - mean;
+    fx_dd_add(hi, lo, d * d);
+  }
+  const double var = fx_dd_warp_total(hi, lo) / (double)(n - 1);
+  const double sd = sqrt(var);
+  if (sd <= 0.0) return 0.0;
+  return (mean / sd) * sqrt(ann);
+}
+
 // ---- the fused step --------------------------------------------------------------------------------------------
 #define FX_OP_KILL 1u
 #define FX_OP_ACTIVATE 2u
@@ -623,7 +673,8 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
       int slot;  // where the new return lands (same rule as fx_sharpe_push)
       if (e.bar_index <= last) slot = 0; else slot = (len == Wn) ? head : (head + len) % Wn;
       const int nn = fx_sharpe_push(ws.ring, 1, Wn, len, head, last, e.bar_index, ret);
-      r = fx_sharpe_eval(ws.ring, 1, Wn, nn, head, c.annualization_factor);
+      __syncwarp();
+      r = fx_sharpe_eval_warp(ws.ring, Wn, nn, head, c.annualization_factor, lane);
       if (lane == 0) {
         gring[slot] = ret;
         st.sh_len[env] = len; st.sh_head[env] = head; st.sh_last_step[env] = last;
