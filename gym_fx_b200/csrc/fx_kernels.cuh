@@ -49,12 +49,17 @@ struct FxKernelParams {
   int32_t fast_features;    // 5: F == n_cols == 5 with identity columns (the [W][5] block is one contiguous span)
 };
 
-#define FX_WARPS 4  // warps (= envs) per CTA of the step kernel
+// warps (= envs) per CTA of the step kernel.  One warp per CTA lets the second wave back-fill SM slots as soon as a
+// single env finishes (measured, cfg2: 4 warps/CTA 26.1 / 64.7 us per step at 4096 / 16384 envs, 2: 25.9 / 64.7,
+// 1: 24.2 / 57.9).
+#ifndef FX_WARPS
+#define FX_WARPS 1
+#endif
 // CTAs per SM the step kernel is compiled for.  Measured on B200 (cfg2, us/step at 4096 / 16384 envs):
-//   8 (64 regs, 220 B of spills) 30.4 / 73.1 | 6: 29.8 / 71.1 | 5: 28.1 / 69.8 | 4 (128 regs, no spills) 26.2 / 65.0 |
-//   3: 28.7 / 75.9.  The spill-free build wins although 4096 envs then run as two waves of 16 warps per SM.
+//   (with 4 warps per CTA) 8 (64 regs, 220 B of spills) 30.4 / 73.1 | 6: 29.8 / 71.1 | 5: 28.1 / 69.8 |
+//   4 (128 regs, no spills) 26.2 / 65.0 | 3: 28.7 / 75.9.  The spill-free build wins although 4096 envs then run as two waves of 16 warps per SM.
 #ifndef FX_MIN_BLOCKS
-#define FX_MIN_BLOCKS 4
+#define FX_MIN_BLOCKS (16 / FX_WARPS)   // 16 warps per SM => 128 registers, no spills
 #endif
 
 // host-callable launchers (fx_kernels.cu)
