@@ -162,7 +162,7 @@ def run_reference(args, rank, world):
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": desc, "total_envs": total,
                    "note": "CPU arm: C port of the reference path (oracle/fxenv_oracle.c); the Python reference "
-                           "(~1.3-1.5k steps/s/process per SURVEY section 6) cannot travel to the GPU box"},
+                           "(measured in the build container over the backtrader shim: 676 steps/s/process at this shape, profiles/r1_reference_python_rate.json) cannot travel to the GPU box"},
         "cpu_baseline": {"value": rate, "unit": "env-steps/s", "cores": used, "kind": "port",
                          "sample": f"{total} envs x {done} steps, {used} host threads (pthreads), each thread runs its env slice without a per-step barrier"},
         "e2e": {"value": rate, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
