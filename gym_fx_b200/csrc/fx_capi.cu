@@ -173,9 +173,10 @@ int fxenv_create(const FxConfig* cfg, FxEnv** out) {
   const size_t ring = (c.reward == FX_REWARD_SHARPE) ? (size_t)c.sharpe_window : 1;
   SlabPlan plan;
   const size_t capP = (size_t)cap + FXO_SLACK;
-  size_t o_d[9], o_start, o_i[11], o_flags, o_ring, o_welford, o_meta, o_p0, o_p1, o_sz;
+  size_t o_d[9], o_start, o_i[11], o_flags, o_ring, o_welford, o_meta, o_p0, o_p1, o_sz, o_nbar;
   for (int i = 0; i < 9; i++) o_d[i] = plan.add(N * 8);
   o_start = plan.add(N * 8);
+  o_nbar = plan.add(N * 6 * 8);
   for (int i = 0; i < 11; i++) o_i[i] = plan.add(N * 4);
   o_flags = plan.add(N * 4);
   o_ring = plan.add(N * ring * 8);
@@ -194,6 +195,7 @@ int fxenv_create(const FxConfig* cfg, FxEnv** out) {
                        &st.commission_paid, &st.dd_peak, &st.sub_need};
   for (int i = 0; i < 9; i++) *dcols[i] = reinterpret_cast<double*>(b + o_d[i]);
   st.start = reinterpret_cast<int64_t*>(b + o_start);
+  st.nbar = reinterpret_cast<double*>(b + o_nbar);
   int32_t** icols[11] = {&st.t, &st.total_bars, &st.position, &st.bar_index, &st.trades, &st.n_orders,
                          &st.sh_len, &st.sh_head, &st.sh_last_step, &st.dd_last_step, &st.n_acc};
   for (int i = 0; i < 11; i++) *icols[i] = reinterpret_cast<int32_t*>(b + o_i[i]);

@@ -207,6 +207,25 @@ FX_HD bool fx_entry_hits(uint32_t meta, double p0, double p1, const FxBar& b) {
   return fx_match_stop(buy, p0, b, px) || fx_match_limit(buy, p1, b, px);
 }
 
+// Same test, also returning the execution price (select form: every lane of a warp evaluates it without divergence).
+// The price is a pure function of (entry, bar) as well, so the FIFO walk only has to fetch it from the owning lane.
+FX_HD bool fx_entry_fill(uint32_t meta, double p0, double p1, const FxBar& b, double& px) {
+  const uint32_t kind = meta & FXO_KIND_MASK;
+  const bool buy = !(meta & FXO_SELL);
+  // stop @p0 (PAIR) -- bbroker.py _try_exec_stop
+  const bool s_open = buy ? (b.o >= p0) : (b.o <= p0);
+  const bool s_hit = s_open || (buy ? (b.h >= p0) : (b.l <= p0));
+  // limit @p0 (PARENT) or @p1 (PAIR) -- bbroker.py _try_exec_limit
+  const double pl = (kind == FXO_PARENT) ? p0 : p1;
+  const bool l_open = buy ? (pl >= b.o) : (pl <= b.o);
+  const bool l_hit = l_open || (buy ? (pl >= b.l) : (pl <= b.h));
+  if (kind == FXO_MARKET) { px = b.o; return true; }
+  if (kind == FXO_PARENT) { px = l_open ? b.o : pl; return l_hit; }
+  if (s_hit) { px = s_open ? b.o : p0; return true; }  // the stop leg is tried first
+  px = l_open ? b.o : pl;
+  return l_hit;
+}
+
 // ---- BackBroker.next, step 0: "while self._toactivate: activate()" -- per entry, lane-parallel on the device ------
 FX_HD uint32_t fx_entry_begin_bar(uint32_t meta) {
   return (meta & FXO_ACTIVATE_NEXT) ? ((meta & ~FXO_ACTIVATE_NEXT) | FXO_ACTIVE) : meta;

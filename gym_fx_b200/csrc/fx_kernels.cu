@@ -363,7 +363,12 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
   const int ring_len = (REWARD == FX_REWARD_SHARPE) ? c.sharpe_window : 0;
   const int win_doubles = fx_window_doubles(c.window_size, C);
   const WarpSmem ws = fx_carve(fx_smem + (size_t)warp * fx_warp_smem_bytes(win_doubles, ring_len), win_doubles, ring_len);
-  fx_window_init(lane, ws);  // mbarrier init + fence now, so that its latency hides behind the state loads
+  // Programmatic dependent launch: let the NEXT kernel of the stream / graph be scheduled while this grid drains (its
+  // CTAs take SM slots as ours exit and park at their own griddepcontrol.wait), which hides the launch gap between
+  // dependent steps.  Everything that touches memory written by the previous kernel comes after the wait below.
+  asm volatile("griddepcontrol.launch_dependents;");
+  fx_window_init(lane, ws);  // mbarrier init + fence
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int capP = P.cap + FXO_SLACK;
   const int pair = (c.num_pairs == 1) ? 0 : env % c.num_pairs;
   const FxPairTable& tb = P.pair[pair];
@@ -401,6 +406,18 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
   float action_raw_f = 0.0f;
   if (c.action_mode == FX_ACTION_CONTINUOUS) action_raw_f = reinterpret_cast<const float*>(actions)[env];
   else action_raw_i = reinterpret_cast<const int32_t*>(actions)[env];
+  // the candle this call works on was saved by the previous call (FxDeviceState::nbar), and the first 32 orders of
+  // the table sit at an address that only depends on the env: both travel in this same round trip
+  const double2* __restrict__ nb2 = reinterpret_cast<const double2*>(st.nbar + (int64_t)env * 6);
+  const double2 nb_oh = nb2[0], nb_lc = nb2[1];
+  const double nb_price = st.nbar[(int64_t)env * 6 + 4];
+  const int64_t obase = (int64_t)env * capP;
+  uint32_t* __restrict__ gmeta = st.o_meta + obase;
+  double* __restrict__ gp0 = st.o_p0 + obase;
+  double* __restrict__ gp1 = st.o_p1 + obase;
+  double* __restrict__ gsz = st.o_sz + obase;
+  uint32_t pm0 = gmeta[lane];
+  double pp0 = gp0[lane], pp1 = gp1[lane], psz = gsz[lane];
 
 #ifdef FXENV_ENABLE_TIMING
   if (tstamp) {  // keep two consecutive steps: slot = parity of the (pre-step) cursor
@@ -422,6 +439,7 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
         st.welford[wi] = tb.candles[start * (int64_t)C + c.feature_cols[lane]];
         st.welford[wi + 1] = 0.0;
       }
+      if (lane < 5) st.nbar[(int64_t)env * 6 + lane] = tb.candles[start * (int64_t)C + (lane < 4 ? lane : c.price_col)];
       if (lane == 0) {
         fx_store_all(st, env, e);
         st.t[env] = 0; st.total_bars[env] = total_bars; st.n_orders[env] = 0; st.n_acc[env] = 0; st.sub_need[env] = 0.0;
@@ -463,16 +481,16 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
   //      in shared memory while the broker runs)
   const int dbg = P.debug;
   const int s_obs = t + 1;  // bar_index after this step
-  const int64_t obase = (int64_t)env * capP;
-  uint32_t* __restrict__ gmeta = st.o_meta + obase;
-  double* __restrict__ gp0 = st.o_p0 + obase;
-  double* __restrict__ gp1 = st.o_p1 + obase;
-  double* __restrict__ gsz = st.o_sz + obase;
-
   const double* __restrict__ row = tb.candles + (start + t) * (int64_t)C;
   FxBar b;
-  b.o = row[0]; b.h = row[1]; b.l = row[2]; b.c = row[3];
-  const double last_price = row[c.price_col];
+  b.o = nb_oh.x; b.h = nb_oh.y; b.l = nb_lc.x; b.c = nb_lc.y;
+  const double last_price = nb_price;
+  // candle of the next call (lanes 0..4), stored with the write-back
+  double nbar_next = 0.0;
+  if (lane < 5) {
+    const int tn = (t + 1 < total_bars) ? t + 1 : total_bars - 1;
+    nbar_next = tb.candles[(start + tn) * (int64_t)C + (lane < 4 ? lane : c.price_col)];
+  }
 
   int hn = 0;
   const bool scale = fx_scaling_active(c, s_obs, hn);
@@ -490,29 +508,12 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
       if (welford_live) wf_x = row[c.feature_cols[lane]];
     }
   }
-  // first chunk of the order table (one order per lane)
-  uint32_t pm0 = 0u;
-  double pp0 = 0.0, pp1 = 0.0, psz = 0.0;
-  if (advance && lane < n && !(dbg & 2)) { pm0 = gmeta[lane]; pp0 = gp0[lane]; pp1 = gp1[lane]; psz = gsz[lane]; }
-
   int win_left = s_obs - c.window_size;
   if (win_left < 0) win_left = 0;
   int win_shift = 0;
   __syncwarp();
   if (!(dbg & 1)) win_shift = fx_window_issue(tb, C, start, win_left, s_obs - win_left, lane, ws);
 
-  // running z-score statistics while the history window is still growing (or expanding_zscore); stats -> smem
-  if (lane < c.n_features) {
-    if (welford_live) {
-      fx_welford_add(wf_m, wf_m2, wf_x, t + 1);
-      const int64_t wi = ((int64_t)env * FXENV_MAX_FEATURES + lane) * 2;
-      st.welford[wi] = wf_m; st.welford[wi + 1] = wf_m2;
-    }
-    if (scale) {
-      if (!table_stats) fx_welford_to_stats(wf_m, wf_m2, hn, st_m, st_r);
-      ws.mean[lane] = st_m; ws.rcp[lane] = st_r;
-    }
-  }
   FX_STAMP_DEP(1, __double_as_longlong(b.o) + __double_as_longlong(b.c));  // the new bar has arrived
 
   if (!(dbg & 2)) {
@@ -543,36 +544,34 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
         int n_fills = 0;
 #endif
         uint32_t carry = 0u;  // operation for the first entry of the next chunk (bracket pair of a parent in lane 31)
+        if (reload0 && lane < n) { pm0 = gmeta[lane]; pp0 = gp0[lane]; pp1 = gp1[lane]; psz = gsz[lane]; }
         for (int k0 = 0; k0 < n; k0 += 32) {
           const int k = k0 + lane;
           const bool valid = k < n;
-          uint32_t m0 = 0u, m = 0u;
-          double p0 = 0.0, p1 = 0.0, sz = 0.0;
+          // the chunk in flight: entries [k0+32, k0+64) are requested now and consumed by the next iteration (this
+          // iteration only writes at indices <= k, so what it fetches stays valid)
+          const uint32_t m0 = pm0;
+          const double p0 = pp0, p1 = pp1, sz = psz;
+          if (k + 32 < n) { pm0 = gmeta[k + 32]; pp0 = gp0[k + 32]; pp1 = gp1[k + 32]; psz = gsz[k + 32]; }
+          uint32_t m = 0u;
           if (valid) {
-            if (k0 == 0 && !reload0) { m0 = pm0; p0 = pp0; p1 = pp1; sz = psz; }
-            else { m0 = gmeta[k]; p0 = gp0[k]; p1 = gp1[k]; sz = gsz[k]; }
             m = fx_entry_begin_bar(m0);
             if (k >= first_sub) m &= ~FXO_SUBMITTED;  // accepted by the cash bound
             if (lane == 0) m = fx_apply_op(m, carry);
           }
           carry = 0u;
-          uint32_t hm = __ballot_sync(FX_FULL, valid && !(m & FXO_DEAD) && fx_entry_hits(m, p0, p1, b));
+          double px_lane = 0.0;  // execution price of this lane's entry, should it trade on this bar
+          const bool hit = fx_entry_fill(m, p0, p1, b, px_lane);
+          uint32_t hm = __ballot_sync(FX_FULL, valid && !(m & FXO_DEAD) && hit);
           while (hm) {
             const int l = __ffs(hm) - 1;
             hm &= hm - 1;
-            const uint32_t bm = __shfl_sync(FX_FULL, m, l);
+            const uint32_t bm = __shfl_sync(FX_FULL, m, l);  // current state: an earlier fill may have changed it
             if (bm & (FXO_DEAD | FXO_SUBMITTED)) continue;
             const uint32_t kind = bm & FXO_KIND_MASK;
-            const bool buy = !(bm & FXO_SELL);
-            const double bp0 = __shfl_sync(FX_FULL, p0, l), bp1 = __shfl_sync(FX_FULL, p1, l);
-            double px = b.o;
-            bool go;
-            if (kind == FXO_MARKET) go = true;
-            else if (kind == FXO_PARENT) go = fx_match_limit(buy, bp0, b, px);
-            else go = (bm & FXO_ACTIVE) && (fx_match_stop(buy, bp0, b, px) || fx_match_limit(buy, bp1, b, px));
-            if (!go) continue;
+            if (kind == FXO_PAIR && !(bm & FXO_ACTIVE)) continue;
             // Completed or Margin: either way the entry leaves the table (a PAIR: sibling / group cancelled)
-            const bool margin = fx_execute(c, e, __shfl_sync(FX_FULL, sz, l), px);
+            const bool margin = fx_execute(c, e, __shfl_sync(FX_FULL, sz, l), __shfl_sync(FX_FULL, px_lane, l));
 #ifdef FXENV_ENABLE_TIMING
             n_fills++;
 #endif
@@ -684,6 +683,7 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
     FX_STAMP(7);  // reward
 
     // ---- write back (lane 0): always-changing columns, then the ones a fill touched
+    if (lane < 5) st.nbar[(int64_t)env * 6 + lane] = nbar_next;
     if (lane == 0) {
       st.t[env] = t; st.flags[env] = e.flags;
       st.equity[env] = e.equity; st.prev_equity[env] = e.prev_equity; st.price[env] = e.price;
@@ -707,6 +707,20 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
   FX_STAMP(8);  // scalars written back
 
   // ---- observation windows (app/env.py:160 -> preprocessor.make_observation) from the staged copy
+  // running z-score statistics while the history window is still growing (or expanding_zscore); stats -> smem.
+  // Consumed only here so that the loads issued before the broker pass never stall it.
+  if (lane < c.n_features) {
+    if (welford_live) {
+      fx_welford_add(wf_m, wf_m2, wf_x, t + 1);
+      const int64_t wi = ((int64_t)env * FXENV_MAX_FEATURES + lane) * 2;
+      st.welford[wi] = wf_m; st.welford[wi + 1] = wf_m2;
+    }
+    if (scale) {
+      if (!table_stats) fx_welford_to_stats(wf_m, wf_m2, hn, st_m, st_r);
+      ws.mean[lane] = st_m; ws.rcp[lane] = st_r;
+    }
+  }
+  __syncwarp();
   if (!(dbg & 1)) {
     fx_window_wait(ws);
     fx_emit_windows<FAST5>(P, lane, s_obs, scale, ws.win + win_shift, ws.mean, ws.rcp, obs_row);
@@ -742,6 +756,7 @@ __global__ void fx_reset_kernel(const __grid_constant__ FxKernelParams P, const 
   st.n_orders[env] = 0;
   st.n_acc[env] = 0;
   st.sub_need[env] = 0.0;
+  for (int j = 0; j < 5; j++) st.nbar[(int64_t)env * 6 + j] = tb.candles[start * (int64_t)c.n_cols + (j < 4 ? j : c.price_col)];
   if (fx_uses_running_stats(c)) {
     for (int f = 0; f < c.n_features; f++) {
       const int64_t wi = ((int64_t)env * FXENV_MAX_FEATURES + f) * 2;
@@ -839,8 +854,14 @@ size_t observe_smem_bytes(const FxKernelParams& P) {
 cudaError_t fx_configure_kernels(const FxKernelParams& P) {
   const size_t smem = step_smem_bytes(P);
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  // ask for enough shared-memory carve-out that FX_MIN_BLOCKS CTAs (+1 KB system use each) fit on an SM
+  const size_t want = (size_t)FX_MIN_BLOCKS * (smem + 1024);
+  int pct = (int)((want * 100 + 228 * 1024 - 1) / (228 * 1024));
+  if (pct > 100) pct = 100;
+  cudaError_t e = cudaFuncSetAttribute(pick_kernel(P), cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  if (e != cudaSuccess) return e;
   if (smem <= 48 * 1024) return cudaSuccess;
-  cudaError_t e = cudaFuncSetAttribute(pick_kernel(P), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  e = cudaFuncSetAttribute(pick_kernel(P), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(fx_observe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)observe_smem_bytes(P));
 }
@@ -848,8 +869,17 @@ cudaError_t fx_configure_kernels(const FxKernelParams& P) {
 cudaError_t fx_launch_step(const FxKernelParams& P, const void* actions, float* obs, float* reward, double* reward64,
                            uint8_t* terminated, cudaStream_t stream) {
   const int blocks = (P.cfg.num_envs + FX_WARPS - 1) / FX_WARPS;
-  pick_kernel(P)<<<blocks, FX_WARPS * 32, step_smem_bytes(P), stream>>>(P, actions, obs, reward, reward64, terminated);
-  return cudaGetLastError();
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3(blocks);
+  lc.blockDim = dim3(FX_WARPS * 32);
+  lc.dynamicSmemBytes = step_smem_bytes(P);
+  lc.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = at;
+  lc.numAttrs = (P.debug & 4) ? 0 : 1;  // FXENV_DEBUG & 4: plain stream-serialised launches (A/B timing only)
+  return cudaLaunchKernelEx(&lc, pick_kernel(P), P, actions, obs, reward, reward64, terminated);
 }
 
 cudaError_t fx_launch_reset(const FxKernelParams& P, const int64_t* start_bar, const uint8_t* mask, int first,

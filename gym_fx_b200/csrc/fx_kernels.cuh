@@ -25,6 +25,9 @@ struct FxDeviceState {
   double *equity, *prev_equity, *price, *commission_paid; // bridge (app/bt_bridge.py:30-66)
   double* dd_peak;                                        // dd_penalized_reward._peak
   double* sub_need;                                       // check_submitted cash bound of the entries [n_acc, n_orders)
+  double* nbar;                                           // [N][6] {open, high, low, close, price_col value, -} of the candle the NEXT step call
+                                                          // works on (row min(t+1, total_bars-1), or row t right after a reset): saves the
+                                                          // dependent cursor -> candle round trip at the head of every step
   int64_t* start;                                         // first bar (table row) of the episode window
   int32_t *t, *total_bars, *position, *bar_index, *trades, *n_orders, *n_acc;
   int32_t *sh_len, *sh_head, *sh_last_step, *dd_last_step;

@@ -58,3 +58,19 @@ print("  fills per env-step: mean %.2f p50 %d p90 %d p99 %d max %d ; table entri
 for lo, hi in ((0, 0), (1, 1), (2, 3), (4, 7), (8, 15), (16, 1000)):
     sel = (nf >= lo) & (nf <= hi)
     if sel.any(): print(f"    fills {lo}-{hi}: {sel.sum():5d} warps, lifetime mean {tot[sel].mean():6.2f} us max {tot[sel].max():6.2f}")
+
+# what would a work-sorted launch order buy?  greedy list scheduling of the measured warp lifetimes on 148 x 16 slots
+import heapq
+def makespan(durs, nslots=148 * 16):
+    h = [0.0] * nslots
+    heapq.heapify(h)
+    end = 0.0
+    for d in durs:
+        s = heapq.heappop(h); heapq.heappush(h, s + d); end = max(end, s + d)
+    return end
+life = (g1 - g0) / 1e3
+print("  list-scheduling model (us): index order %.1f | sorted by table entries desc %.1f | by fills desc %.1f | by lifetime desc (ideal) %.1f | sum/slots %.1f | max %.1f"
+      % (makespan(life), makespan(life[np.argsort(-ntab, kind='stable')]), makespan(life[np.argsort(-nf, kind='stable')]),
+         makespan(np.sort(life)[::-1]), life.sum() / (148 * 16), life.max()))
+os.makedirs("gpurun_out", exist_ok=True)
+np.savez_compressed(f"gpurun_out/phase_{wl}_{N}.npz", stamps=buf2)
