@@ -189,6 +189,9 @@ int fxenv_create(const FxConfig* cfg, FxEnv** out) {
   ce = cudaMalloc(&env->slab, plan.bytes);
   if (ce != cudaSuccess) { delete env; return cuda_fail(nullptr, ce, "cudaMalloc(state slab)"); }
   cudaMemset(env->slab, 0, plan.bytes);
+  ce = cudaMalloc(&env->P.seq, N * sizeof(int32_t));
+  if (ce != cudaSuccess) { delete env; return cuda_fail(nullptr, ce, "cudaMalloc(seq)"); }
+  cudaMemset(env->P.seq, 0, N * sizeof(int32_t));
   FxDeviceState& st = env->P.st;
   unsigned char* b = env->slab;
   double** dcols[9] = {&st.cash, &st.psize, &st.pprice, &st.equity, &st.prev_equity, &st.price,
@@ -218,6 +221,7 @@ int fxenv_destroy(FxEnv* env) {
     cudaFree(env->candles_dev[p]); cudaFree(env->stats_dev[p]); cudaFree(env->minutes_dev[p]);
   }
   cudaFree(env->slab);
+  cudaFree(env->P.seq);
   cudaFree(env->P.timing);
   cudaFree(env->h_actions); cudaFree(env->h_obs); cudaFree(env->h_reward); cudaFree(env->h_term);
   if (env->hstream) cudaStreamDestroy(env->hstream);
@@ -290,7 +294,7 @@ int fxenv_step(FxEnv* env, const void* actions_dev, float* obs_dev, float* rewar
   if (rc) return rc;
   if (!actions_dev || !obs_dev || !reward_dev || !terminated_dev) return fail(env, FXENV_E_INVALID, "null I/O pointer");
   DeviceGuard g(env->device);
-  FX_CUDA(env, fx_launch_step(env->P, actions_dev, obs_dev, reward_dev, reward64_dev, terminated_dev, (cudaStream_t)stream));
+  FX_CUDA(env, fx_launch_step(env->P, actions_dev, obs_dev, reward_dev, reward64_dev, terminated_dev, -1, (cudaStream_t)stream));
   env->launches++;
   return FXENV_OK;
 }
@@ -308,7 +312,7 @@ int fxenv_step_many(FxEnv* env, int n_steps, const void* actions_dev, float* obs
     for (int k = 0; k < n_steps; k++) {
       const char* a = reinterpret_cast<const char*>(actions_dev) + (size_t)k * N * 4;
       cudaError_t e = fx_launch_step(env->P, a, obs_dev + (size_t)(k % obs_slots) * N * D, reward_dev + (size_t)k * N,
-                                     nullptr, terminated_dev + (size_t)k * N, s);
+                                     nullptr, terminated_dev + (size_t)k * N, n_steps > 1 ? k : -1, s);
       if (e != cudaSuccess) return e;
     }
     return cudaSuccess;
@@ -357,7 +361,7 @@ int fxenv_step_host(FxEnv* env, const void* actions_host, float* obs_host, float
   }
   cudaStream_t s = env->hstream;
   FX_CUDA(env, cudaMemcpyAsync(env->h_actions, actions_host, N * 4, cudaMemcpyHostToDevice, s));
-  FX_CUDA(env, fx_launch_step(env->P, env->h_actions, env->h_obs, env->h_reward, nullptr, env->h_term, s));
+  FX_CUDA(env, fx_launch_step(env->P, env->h_actions, env->h_obs, env->h_reward, nullptr, env->h_term, -1, s));
   env->launches++;
   FX_CUDA(env, cudaMemcpyAsync(obs_host, env->h_obs, N * D * 4, cudaMemcpyDeviceToHost, s));
   FX_CUDA(env, cudaMemcpyAsync(reward_host, env->h_reward, N * 4, cudaMemcpyDeviceToHost, s));

@@ -31,7 +31,7 @@ namespace {
 
 // per-warp shared memory: the TMA-staged candle window + z-score statistics (+ the Sharpe ring) + one mbarrier
 struct WarpSmem {
-  double *win, *mean, *rcp, *ring;
+  double *win, *stat, *ring;  // stat: [F][2] = {mean, 1/std} per feature (the layout of the per-bar statistics table)
   unsigned long long* bar;
 };
 
@@ -46,8 +46,7 @@ __device__ __forceinline__ WarpSmem fx_carve(unsigned char* base, int win_double
   WarpSmem w;
   double* d = reinterpret_cast<double*>(base);
   w.win = d; d += win_doubles;
-  w.mean = d; d += FXENV_MAX_FEATURES;
-  w.rcp = d; d += FXENV_MAX_FEATURES;
+  w.stat = d; d += 2 * FXENV_MAX_FEATURES;
   w.ring = d; d += ring_len;
   w.bar = reinterpret_cast<unsigned long long*>(d);
   return w;
@@ -66,16 +65,20 @@ __device__ __forceinline__ void fx_window_init(int lane, const WarpSmem& ws) {
 }
 
 __device__ __forceinline__ int fx_window_issue(const FxPairTable& tb, int C, int64_t start, int left, int have, int lane,
-                                               const WarpSmem& ws) {
+                                               const WarpSmem& ws, const double* stats_row = nullptr, int n_features = 0) {
   const int64_t e0 = (start + left) * (int64_t)C;
   const int shift = (int)(e0 & 1);
   const unsigned bytes = (unsigned)(((have * C + shift + 1) & ~1) * 8);
   if (lane == 0) {
     const unsigned bar_a = (unsigned)__cvta_generic_to_shared(ws.bar);
     const unsigned dst_a = (unsigned)__cvta_generic_to_shared(ws.win);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+    const unsigned sbytes = stats_row ? (unsigned)n_features * 16u : 0u;  // {mean, 1/std} rows are 16-byte multiples
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes + sbytes) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst_a), "l"(tb.candles + (e0 - shift)), "r"(bytes), "r"(bar_a) : "memory");
+    if (stats_row)  // the bar's z-score statistics ride on the same mbarrier: no register ever holds them
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"((unsigned)__cvta_generic_to_shared(ws.stat)), "l"(stats_row), "r"(sbytes), "r"(bar_a) : "memory");
   }
   return shift;
 }
@@ -139,7 +142,7 @@ __device__ __forceinline__ void fx_welford_to_stats(double wm, double wm2, int h
 
 // self-contained version for the paths that are not latency critical (terminated envs, observe kernel)
 __device__ __forceinline__ bool fx_prepare_stats(const FxKernelParams& P, const FxPairTable& tb, int env, int lane, int s,
-                                                 int64_t start, double* smean, double* srcp) {
+                                                 int64_t start, double* sstat) {
   const FxConfig& c = P.cfg;
   int hn;
   if (!fx_scaling_active(c, s, hn)) return false;
@@ -152,7 +155,7 @@ __device__ __forceinline__ bool fx_prepare_stats(const FxKernelParams& P, const 
       const int64_t wi = ((int64_t)env * FXENV_MAX_FEATURES + lane) * 2;
       fx_welford_to_stats(P.st.welford[wi], P.st.welford[wi + 1], hn, m, r);
     }
-    smean[lane] = m; srcp[lane] = r;
+    sstat[2 * lane] = m; sstat[2 * lane + 1] = r;
   }
   __syncwarp();
   return true;
@@ -170,7 +173,7 @@ __device__ __forceinline__ float fx_finish_t(float v, float clipf) {
 
 template <bool FAST5, bool CLIP>
 __device__ __noinline__ void fx_emit_windows_t(const FxKernelParams& P, int lane, int s, bool scale,
-                                               const double* __restrict__ win, const double* smean, const double* srcp,
+                                               const double* __restrict__ win, const double* sstat,
                                                float* __restrict__ out) {
   const FxConfig& c = P.cfg;
   const int W = c.window_size, C = c.n_cols;
@@ -189,8 +192,8 @@ __device__ __noinline__ void fx_emit_windows_t(const FxKernelParams& P, int lane
       if (lane < 30) {
         const int f0 = (2 * lane) % 5, f1 = (2 * lane + 1) % 5;
         const bool z0 = scale && !c.feature_binary[f0], z1 = scale && !c.feature_binary[f1];
-        const double m0 = z0 ? smean[f0] : 0.0, r0 = z0 ? srcp[f0] : 1.0;
-        const double m1 = z1 ? smean[f1] : 0.0, r1 = z1 ? srcp[f1] : 1.0;
+        const double m0 = z0 ? sstat[2 * f0] : 0.0, r0 = z0 ? sstat[2 * f0 + 1] : 1.0;
+        const double m1 = z1 ? sstat[2 * f1] : 0.0, r1 = z1 ? sstat[2 * f1 + 1] : 1.0;
         const int npair = total >> 1;  // total = 5 W; an odd W leaves one tail element
 #pragma unroll 4
         for (int q = lane; q < npair; q += 30) {
@@ -204,7 +207,7 @@ __device__ __noinline__ void fx_emit_windows_t(const FxKernelParams& P, int lane
           const int j = total - 1, f = j % 5;
           const bool z = scale && !c.feature_binary[f];
           const double x = win[j];
-          __stcs(out + j, fx_finish_t<CLIP>(z ? (float)((x - smean[f]) * srcp[f]) : (float)x, clipf));
+          __stcs(out + j, fx_finish_t<CLIP>(z ? (float)((x - sstat[2 * f]) * sstat[2 * f + 1]) : (float)x, clipf));
         }
       }
     } else {
@@ -215,7 +218,7 @@ __device__ __noinline__ void fx_emit_windows_t(const FxKernelParams& P, int lane
         int k = w - pad;
         if (k < 0) k = 0;
         const double x = win[k * C + c.feature_cols[f]];
-        const float v = (scale && !c.feature_binary[f]) ? (float)((x - smean[f]) * srcp[f]) : (float)x;
+        const float v = (scale && !c.feature_binary[f]) ? (float)((x - sstat[2 * f]) * sstat[2 * f + 1]) : (float)x;
         __stcs(out + j, fx_finish_t<CLIP>(v, clipf));
         w += dw; f += df;
         if (f >= F) { f -= F; w += 1; }
@@ -243,10 +246,10 @@ __device__ __noinline__ void fx_emit_windows_t(const FxKernelParams& P, int lane
 
 template <bool FAST5>
 __device__ __forceinline__ void fx_emit_windows(const FxKernelParams& P, int lane, int s, bool scale,
-                                                const double* __restrict__ win, const double* smean, const double* srcp,
+                                                const double* __restrict__ win, const double* sstat,
                                                 float* __restrict__ out) {
-  if (P.cfg.feature_clip > 0.0) fx_emit_windows_t<FAST5, true>(P, lane, s, scale, win, smean, srcp, out);
-  else fx_emit_windows_t<FAST5, false>(P, lane, s, scale, win, smean, srcp, out);
+  if (P.cfg.feature_clip > 0.0) fx_emit_windows_t<FAST5, true>(P, lane, s, scale, win, sstat, out);
+  else fx_emit_windows_t<FAST5, false>(P, lane, s, scale, win, sstat, out);
 }
 
 // issue + wait + emit in one go (terminated path, observe kernel)
@@ -259,9 +262,9 @@ __device__ __forceinline__ void fx_stream_windows(const FxKernelParams& P, const
   fx_window_init(lane, ws);
   __syncwarp();
   const int shift = fx_window_issue(tb, P.cfg.n_cols, start, left, s - left, lane, ws);
-  const bool scale = fx_prepare_stats(P, tb, env, lane, s, start, ws.mean, ws.rcp);
+  const bool scale = fx_prepare_stats(P, tb, env, lane, s, start, ws.stat);
   fx_window_wait(ws);
-  fx_emit_windows<FAST5>(P, lane, s, scale, ws.win + shift, ws.mean, ws.rcp, out);
+  fx_emit_windows<FAST5>(P, lane, s, scale, ws.win + shift, ws.stat, out);
 }
 
 __device__ __forceinline__ int fx_scalar_offset(const FxConfig& c) {
@@ -349,26 +352,14 @@ __device__ __forceinline__ uint32_t fx_apply_op(uint32_t m, uint32_t op) {
   return m;
 }
 
+// One env-step of one env by one warp (everything between the cross-kernel dependency wait and the release).
 template <int STRAT, int REWARD, bool FAST5>
-__global__ void __launch_bounds__(FX_WARPS * 32, FX_MIN_BLOCKS)
-fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict__ actions, float* __restrict__ obs,
-               float* __restrict__ reward, double* __restrict__ reward64, uint8_t* __restrict__ terminated) {
-  extern __shared__ __align__(16) unsigned char fx_smem[];
+__device__ __forceinline__ void fx_step_env(const FxKernelParams& P, const void* __restrict__ actions, float* __restrict__ obs,
+                                            float* __restrict__ reward, double* __restrict__ reward64,
+                                            uint8_t* __restrict__ terminated, const int env, const int lane, const WarpSmem& ws) {
   const FxConfig& c = P.cfg;
   const FxDeviceState& st = P.st;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int env = blockIdx.x * FX_WARPS + warp;
-  if (env >= c.num_envs) return;
   const int C = c.n_cols;
-  const int ring_len = (REWARD == FX_REWARD_SHARPE) ? c.sharpe_window : 0;
-  const int win_doubles = fx_window_doubles(c.window_size, C);
-  const WarpSmem ws = fx_carve(fx_smem + (size_t)warp * fx_warp_smem_bytes(win_doubles, ring_len), win_doubles, ring_len);
-  // Programmatic dependent launch: let the NEXT kernel of the stream / graph be scheduled while this grid drains (its
-  // CTAs take SM slots as ours exit and park at their own griddepcontrol.wait), which hides the launch gap between
-  // dependent steps.  Everything that touches memory written by the previous kernel comes after the wait below.
-  asm volatile("griddepcontrol.launch_dependents;");
-  fx_window_init(lane, ws);  // mbarrier init + fence
-  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int capP = P.cap + FXO_SLACK;
   const int pair = (c.num_pairs == 1) ? 0 : env % c.num_pairs;
   const FxPairTable& tb = P.pair[pair];
@@ -400,8 +391,6 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
   e.cash = st.cash[env]; e.psize = st.psize[env]; e.pprice = st.pprice[env]; e.equity = st.equity[env];
   e.commission_paid = st.commission_paid[env]; e.trades = st.trades[env];
   e.value = e.equity;
-  const double cash0 = e.cash, psize0 = e.psize, pprice0 = e.pprice, comm0 = e.commission_paid;
-  const int32_t trades0 = e.trades;
   int action_raw_i = 0;
   float action_raw_f = 0.0f;
   if (c.action_mode == FX_ACTION_CONTINUOUS) action_raw_f = reinterpret_cast<const float*>(actions)[env];
@@ -462,9 +451,9 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
       if (left < 0) left = 0;
       __syncwarp();
       const int shift = fx_window_issue(tb, C, start, left, s - left, lane, ws);
-      const bool scale = fx_prepare_stats(P, tb, env, lane, s, start, ws.mean, ws.rcp);
+      const bool scale = fx_prepare_stats(P, tb, env, lane, s, start, ws.stat);
       fx_window_wait(ws);
-      fx_emit_windows<FAST5>(P, lane, s, scale, ws.win + shift, ws.mean, ws.rcp, obs_row);
+      fx_emit_windows<FAST5>(P, lane, s, scale, ws.win + shift, ws.stat, obs_row);
     }
     return;
   }
@@ -476,48 +465,34 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
   else { t += 1; advance = true; }
   e.flags = flags;
 
-  // ---- round trip 2: everything that only needs the cursor is requested together -- the new bar, the z-score
-  //      statistics, the first 32 orders of the table, and the TMA bulk copy of the observation window (which lands
-  //      in shared memory while the broker runs)
+  // ---- the broker can start right away (candle + first 32 orders arrived with the state); what only the observation
+  //      needs -- the candle window and the bar's z-score statistics -- is fetched by TMA bulk copies into shared
+  //      memory while the broker runs, without occupying registers
   const int dbg = P.debug;
   const int s_obs = t + 1;  // bar_index after this step
   const double* __restrict__ row = tb.candles + (start + t) * (int64_t)C;
   FxBar b;
   b.o = nb_oh.x; b.h = nb_oh.y; b.l = nb_lc.x; b.c = nb_lc.y;
   const double last_price = nb_price;
-  // candle of the next call (lanes 0..4), stored with the write-back
-  double nbar_next = 0.0;
-  if (lane < 5) {
-    const int tn = (t + 1 < total_bars) ? t + 1 : total_bars - 1;
-    nbar_next = tb.candles[(start + tn) * (int64_t)C + (lane < 4 ? lane : c.price_col)];
-  }
-
   int hn = 0;
   const bool scale = fx_scaling_active(c, s_obs, hn);
   const bool table_stats = scale && fx_stats_from_table(c, tb, hn);
   const bool welford_live = advance && fx_uses_running_stats(c) && (c.scaling == FX_SCALING_EXPANDING || t + 1 <= c.scaling_window);
-  double st_m = 0.0, st_r = 1.0, wf_m = 0.0, wf_m2 = 0.0, wf_x = 0.0;
-  if (lane < c.n_features) {
-    if (table_stats) {
-      const double* sp = tb.stats + ((start + t) * (int64_t)c.n_features + lane) * 2;
-      st_m = sp[0]; st_r = sp[1];
-    }
-    if (welford_live || (scale && !table_stats)) {
-      const int64_t wi = ((int64_t)env * FXENV_MAX_FEATURES + lane) * 2;
-      wf_m = st.welford[wi]; wf_m2 = st.welford[wi + 1];
-      if (welford_live) wf_x = row[c.feature_cols[lane]];
-    }
-  }
+
   int win_left = s_obs - c.window_size;
   if (win_left < 0) win_left = 0;
   int win_shift = 0;
   __syncwarp();
-  if (!(dbg & 1)) win_shift = fx_window_issue(tb, C, start, win_left, s_obs - win_left, lane, ws);
+  if (!(dbg & 1))  // the observation window and (steady state) the bar's z-score statistics: TMA -> shared memory
+    win_shift = fx_window_issue(tb, C, start, win_left, s_obs - win_left, lane, ws,
+                                table_stats ? tb.stats + (start + t) * (int64_t)c.n_features * 2 : nullptr, c.n_features);
 
   FX_STAMP_DEP(1, __double_as_longlong(b.o) + __double_as_longlong(b.c));  // the new bar has arrived
 
+  double nbar_next = 0.0;
   if (!(dbg & 2)) {
     int n_live = n;
+    bool any_fill = false;  // cash / position / commission / trade counters only change when an order executes
 
     if (advance) {
       if (n > 0) {
@@ -572,6 +547,7 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
             if (kind == FXO_PAIR && !(bm & FXO_ACTIVE)) continue;
             // Completed or Margin: either way the entry leaves the table (a PAIR: sibling / group cancelled)
             const bool margin = fx_execute(c, e, __shfl_sync(FX_FULL, sz, l), __shfl_sync(FX_FULL, px_lane, l));
+            any_fill = true;
 #ifdef FXENV_ENABLE_TIMING
             n_fills++;
 #endif
@@ -599,6 +575,11 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
       fx_mark_to_market(c, e, b.c);
     }
     FX_STAMP(5);  // broker pass done, marked to market
+    // candle of the next call (lanes 0..4): requested now, stored after the observation has been emitted
+    if (lane < 5) {
+      const int tn = (t + 1 < total_bars) ? t + 1 : total_bars - 1;
+      nbar_next = tb.candles[(start + tn) * (int64_t)C + (lane < 4 ? lane : c.price_col)];
+    }
 
     double r;
     int n_final = n_live, n_acc_new = n_live;
@@ -683,16 +664,14 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
     FX_STAMP(7);  // reward
 
     // ---- write back (lane 0): always-changing columns, then the ones a fill touched
-    if (lane < 5) st.nbar[(int64_t)env * 6 + lane] = nbar_next;
     if (lane == 0) {
       st.t[env] = t; st.flags[env] = e.flags;
       st.equity[env] = e.equity; st.prev_equity[env] = e.prev_equity; st.price[env] = e.price;
       st.position[env] = e.position; st.bar_index[env] = e.bar_index;
-      if (e.cash != cash0) st.cash[env] = e.cash;
-      if (e.psize != psize0) st.psize[env] = e.psize;
-      if (e.pprice != pprice0) st.pprice[env] = e.pprice;
-      if (e.commission_paid != comm0) st.commission_paid[env] = e.commission_paid;
-      if (e.trades != trades0) st.trades[env] = e.trades;
+      if (any_fill) {
+        st.cash[env] = e.cash; st.psize[env] = e.psize; st.pprice[env] = e.pprice;
+        st.commission_paid[env] = e.commission_paid; st.trades[env] = e.trades;
+      }
       if (n_final != n) st.n_orders[env] = n_final;
       if (n_acc_new != n_acc) st.n_acc[env] = n_acc_new;
       if (sub_need_new != sub_need) st.sub_need[env] = sub_need_new;
@@ -707,29 +686,87 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
   FX_STAMP(8);  // scalars written back
 
   // ---- observation windows (app/env.py:160 -> preprocessor.make_observation) from the staged copy
-  // running z-score statistics while the history window is still growing (or expanding_zscore); stats -> smem.
-  // Consumed only here so that the loads issued before the broker pass never stall it.
-  if (lane < c.n_features) {
+  // running z-score statistics while the history window is still growing (or expanding_zscore): warm-up path, one
+  // extra round trip here instead of registers held across the broker pass
+  if (lane < c.n_features && (welford_live || (scale && !table_stats))) {
+    const int64_t wi = ((int64_t)env * FXENV_MAX_FEATURES + lane) * 2;
+    double wf_m = st.welford[wi], wf_m2 = st.welford[wi + 1];
     if (welford_live) {
-      fx_welford_add(wf_m, wf_m2, wf_x, t + 1);
-      const int64_t wi = ((int64_t)env * FXENV_MAX_FEATURES + lane) * 2;
+      fx_welford_add(wf_m, wf_m2, row[c.feature_cols[lane]], t + 1);
       st.welford[wi] = wf_m; st.welford[wi + 1] = wf_m2;
     }
-    if (scale) {
-      if (!table_stats) fx_welford_to_stats(wf_m, wf_m2, hn, st_m, st_r);
-      ws.mean[lane] = st_m; ws.rcp[lane] = st_r;
+    if (scale && !table_stats) {
+      double st_m, st_r;
+      fx_welford_to_stats(wf_m, wf_m2, hn, st_m, st_r);
+      ws.stat[2 * lane] = st_m; ws.stat[2 * lane + 1] = st_r;
     }
   }
   __syncwarp();
   if (!(dbg & 1)) {
     fx_window_wait(ws);
-    fx_emit_windows<FAST5>(P, lane, s_obs, scale, ws.win + win_shift, ws.mean, ws.rcp, obs_row);
+    fx_emit_windows<FAST5>(P, lane, s_obs, scale, ws.win + win_shift, ws.stat, obs_row);
   }
+  if (lane < 5 && !(dbg & 2)) st.nbar[(int64_t)env * 6 + lane] = nbar_next;
   FX_STAMP(9);
   FX_STAMP_GLOBAL(11);
 #undef FX_STAMP
 #undef FX_STAMP_DEP
 #undef FX_STAMP_GLOBAL
+}
+
+__device__ __forceinline__ int fx_ld_acquire(const int32_t* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fx_st_release(int32_t* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
+// The step kernel: one warp per env.  `chain` says how this launch depends on the kernel before it in the stream/graph
+// (all launches carry the programmatic-dependent-launch attribute, so the next kernel can be scheduled while this grid
+// drains):
+//   chain < 0   single step (fxenv_step): griddepcontrol.wait = the whole previous grid has completed and flushed.
+//   chain == 0  first step of a fxenv_step_many batch: same wait, then the env's sequence word is re-based to 0 BEFORE
+//               the dependents may launch, and set to 1 when the env-step is done.
+//   chain = j   j-th step of the batch: envs only depend on THEIR OWN previous step (the actions of the whole batch
+//               were supplied up front), so the warp waits for seq[env] == j (acquire), does the step, and publishes
+//               j + 1 (release).  The light envs of step j+1 thus run under the tail of the heavy envs of step j.
+//               No deadlock: a grid launches only after every CTA of its predecessor is resident (has executed
+//               launch_dependents), so each waiting warp waits for a warp that is already running.
+template <int STRAT, int REWARD, bool FAST5, bool CHAINED>
+__global__ void __launch_bounds__(FX_WARPS * 32, FX_MIN_BLOCKS)
+fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict__ actions, float* __restrict__ obs,
+               float* __restrict__ reward, double* __restrict__ reward64, uint8_t* __restrict__ terminated, const int chain) {
+  extern __shared__ __align__(16) unsigned char fx_smem[];
+  const FxConfig& c = P.cfg;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int env = blockIdx.x * FX_WARPS + warp;
+  if (env >= c.num_envs) return;
+  const int ring_len = (REWARD == FX_REWARD_SHARPE) ? c.sharpe_window : 0;
+  const int win_doubles = fx_window_doubles(c.window_size, c.n_cols);
+  const WarpSmem ws = fx_carve(fx_smem + (size_t)warp * fx_warp_smem_bytes(win_doubles, ring_len), win_doubles, ring_len);
+  if (!CHAINED) {
+    asm volatile("griddepcontrol.launch_dependents;");
+    fx_window_init(lane, ws);  // mbarrier init + fence
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+  } else if (chain == 0) {
+    fx_window_init(lane, ws);
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (lane == 0) { *reinterpret_cast<volatile int32_t*>(P.seq + env) = 0; __threadfence(); }
+    __syncwarp();
+    asm volatile("griddepcontrol.launch_dependents;");
+  } else {
+    asm volatile("griddepcontrol.launch_dependents;");
+    fx_window_init(lane, ws);
+    if (lane == 0) { while (fx_ld_acquire(P.seq + env) != chain) __nanosleep(32); }
+    __syncwarp();
+  }
+  fx_step_env<STRAT, REWARD, FAST5>(P, actions, obs, reward, reward64, terminated, env, lane, ws);
+  if (CHAINED) {
+    __syncwarp();
+    if (lane == 0) fx_st_release(P.seq + (blockIdx.x * FX_WARPS + (threadIdx.x >> 5)), chain + 1);
+  }
 }
 
 __global__ void fx_reset_kernel(const __grid_constant__ FxKernelParams P, const int64_t* __restrict__ start_bar,
@@ -814,28 +851,29 @@ __global__ void fx_stats_kernel(FxConfig c, const double* __restrict__ candles, 
   stats[idx * 2 + 1] = rc;
 }
 
-typedef void (*StepKernel)(const FxKernelParams, const void*, float*, float*, double*, uint8_t*);
+typedef void (*StepKernel)(const FxKernelParams, const void*, float*, float*, double*, uint8_t*, int);
 
 template <int STRAT, int REWARD>
-StepKernel pick_fast(bool fast5) {
-  return fast5 ? fx_step_kernel<STRAT, REWARD, true> : fx_step_kernel<STRAT, REWARD, false>;
+StepKernel pick_fast(bool fast5, bool chained) {
+  if (chained) return fast5 ? fx_step_kernel<STRAT, REWARD, true, true> : fx_step_kernel<STRAT, REWARD, false, true>;
+  return fast5 ? fx_step_kernel<STRAT, REWARD, true, false> : fx_step_kernel<STRAT, REWARD, false, false>;
 }
 
 template <int STRAT>
-StepKernel pick_reward(int reward, bool fast5) {
+StepKernel pick_reward(int reward, bool fast5, bool chained) {
   switch (reward) {
-    case FX_REWARD_PNL: return pick_fast<STRAT, FX_REWARD_PNL>(fast5);
-    case FX_REWARD_SHARPE: return pick_fast<STRAT, FX_REWARD_SHARPE>(fast5);
-    default: return pick_fast<STRAT, FX_REWARD_DD>(fast5);
+    case FX_REWARD_PNL: return pick_fast<STRAT, FX_REWARD_PNL>(fast5, chained);
+    case FX_REWARD_SHARPE: return pick_fast<STRAT, FX_REWARD_SHARPE>(fast5, chained);
+    default: return pick_fast<STRAT, FX_REWARD_DD>(fast5, chained);
   }
 }
 
-StepKernel pick_kernel(const FxKernelParams& P) {
+StepKernel pick_kernel(const FxKernelParams& P, bool chained) {
   const bool fast5 = P.fast_features == 5;
   switch (P.cfg.strategy) {
-    case FX_STRATEGY_DEFAULT: return pick_reward<FX_STRATEGY_DEFAULT>(P.cfg.reward, fast5);
-    case FX_STRATEGY_FIXED_SLTP: return pick_reward<FX_STRATEGY_FIXED_SLTP>(P.cfg.reward, fast5);
-    default: return pick_reward<FX_STRATEGY_ATR_SLTP>(P.cfg.reward, fast5);
+    case FX_STRATEGY_DEFAULT: return pick_reward<FX_STRATEGY_DEFAULT>(P.cfg.reward, fast5, chained);
+    case FX_STRATEGY_FIXED_SLTP: return pick_reward<FX_STRATEGY_FIXED_SLTP>(P.cfg.reward, fast5, chained);
+    default: return pick_reward<FX_STRATEGY_ATR_SLTP>(P.cfg.reward, fast5, chained);
   }
 }
 
@@ -858,16 +896,20 @@ cudaError_t fx_configure_kernels(const FxKernelParams& P) {
   const size_t want = (size_t)FX_MIN_BLOCKS * (smem + 1024);
   int pct = (int)((want * 100 + 228 * 1024 - 1) / (228 * 1024));
   if (pct > 100) pct = 100;
-  cudaError_t e = cudaFuncSetAttribute(pick_kernel(P), cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-  if (e != cudaSuccess) return e;
+  for (int chained = 0; chained < 2; chained++) {
+    cudaError_t e = cudaFuncSetAttribute(pick_kernel(P, chained), cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    if (e != cudaSuccess) return e;
+    if (smem > 48 * 1024) {
+      e = cudaFuncSetAttribute(pick_kernel(P, chained), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+    }
+  }
   if (smem <= 48 * 1024) return cudaSuccess;
-  e = cudaFuncSetAttribute(pick_kernel(P), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(fx_observe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)observe_smem_bytes(P));
 }
 
 cudaError_t fx_launch_step(const FxKernelParams& P, const void* actions, float* obs, float* reward, double* reward64,
-                           uint8_t* terminated, cudaStream_t stream) {
+                           uint8_t* terminated, int chain, cudaStream_t stream) {
   const int blocks = (P.cfg.num_envs + FX_WARPS - 1) / FX_WARPS;
   cudaLaunchConfig_t lc = {};
   lc.gridDim = dim3(blocks);
@@ -879,7 +921,8 @@ cudaError_t fx_launch_step(const FxKernelParams& P, const void* actions, float* 
   at[0].val.programmaticStreamSerializationAllowed = 1;
   lc.attrs = at;
   lc.numAttrs = (P.debug & 4) ? 0 : 1;  // FXENV_DEBUG & 4: plain stream-serialised launches (A/B timing only)
-  return cudaLaunchKernelEx(&lc, pick_kernel(P), P, actions, obs, reward, reward64, terminated);
+  if (lc.numAttrs == 0 || (P.debug & 8)) chain = -1;  // FXENV_DEBUG & 8: grid-serialised steps inside step_many (A/B timing)
+  return cudaLaunchKernelEx(&lc, pick_kernel(P, chain >= 0), P, actions, obs, reward, reward64, terminated, chain);
 }
 
 cudaError_t fx_launch_reset(const FxKernelParams& P, const int64_t* start_bar, const uint8_t* mask, int first,

@@ -45,6 +45,7 @@ struct FxKernelParams {
   FxPairTable pair[FXENV_MAX_PAIRS];
   FxDeviceState st;
   double inv_initial_cash;  // 1 / (initial_cash or 1.0)
+  int32_t* seq;             // [N] per-env sequence word of a fxenv_step_many batch (see fx_step_kernel)
   long long* timing;        // debug (FXENV_TIMING=1): [N][FX_NSTAMP] clock64() phase stamps of the last step, else nullptr
   int32_t obs_dim;
   int32_t cap;              // logical order-table capacity (multiple of 32); arrays hold cap + FXO_SLACK
@@ -67,7 +68,7 @@ struct FxKernelParams {
 
 // host-callable launchers (fx_kernels.cu)
 cudaError_t fx_launch_step(const FxKernelParams& P, const void* actions, float* obs, float* reward, double* reward64,
-                           uint8_t* terminated, cudaStream_t stream);
+                           uint8_t* terminated, int chain, cudaStream_t stream);
 cudaError_t fx_launch_reset(const FxKernelParams& P, const int64_t* start_bar, const uint8_t* mask, int first,
                             cudaStream_t stream);
 cudaError_t fx_launch_observe(const FxKernelParams& P, float* obs, cudaStream_t stream);
