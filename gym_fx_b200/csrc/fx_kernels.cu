@@ -83,13 +83,14 @@ __device__ __forceinline__ int fx_window_issue(const FxPairTable& tb, int C, int
   return shift;
 }
 
-__device__ __forceinline__ void fx_window_wait(const WarpSmem& ws) {
+// `phase` = how many copies this warp's mbarrier has completed before (a persistent warp reuses it for every env-step)
+__device__ __forceinline__ void fx_window_wait(const WarpSmem& ws, unsigned phase = 0u) {
   __syncwarp();
   const unsigned bar_a = (unsigned)__cvta_generic_to_shared(ws.bar);
   unsigned ok = 0;
   while (!ok)
-    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
-                 : "=r"(ok) : "r"(bar_a) : "memory");
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(bar_a), "r"(phase & 1u) : "memory");
 }
 
 // GymFxEnv.reset (app/env.py:102-129): fresh bridge/broker/strategy; broker.next() on bar 0 with nothing pending
@@ -356,7 +357,8 @@ __device__ __forceinline__ uint32_t fx_apply_op(uint32_t m, uint32_t op) {
 template <int STRAT, int REWARD, bool FAST5>
 __device__ __forceinline__ void fx_step_env(const FxKernelParams& P, const void* __restrict__ actions, float* __restrict__ obs,
                                             float* __restrict__ reward, double* __restrict__ reward64,
-                                            uint8_t* __restrict__ terminated, const int env, const int lane, const WarpSmem& ws) {
+                                            uint8_t* __restrict__ terminated, const int env, const int lane, const WarpSmem& ws,
+                                            const unsigned phase = 0u) {
   const FxConfig& c = P.cfg;
   const FxDeviceState& st = P.st;
   const int C = c.n_cols;
@@ -452,7 +454,7 @@ __device__ __forceinline__ void fx_step_env(const FxKernelParams& P, const void*
       __syncwarp();
       const int shift = fx_window_issue(tb, C, start, left, s - left, lane, ws);
       const bool scale = fx_prepare_stats(P, tb, env, lane, s, start, ws.stat);
-      fx_window_wait(ws);
+      fx_window_wait(ws, phase);
       fx_emit_windows<FAST5>(P, lane, s, scale, ws.win + shift, ws.stat, obs_row);
     }
     return;
@@ -703,7 +705,7 @@ __device__ __forceinline__ void fx_step_env(const FxKernelParams& P, const void*
   }
   __syncwarp();
   if (!(dbg & 1)) {
-    fx_window_wait(ws);
+    fx_window_wait(ws, phase);
     fx_emit_windows<FAST5>(P, lane, s_obs, scale, ws.win + win_shift, ws.stat, obs_row);
   }
   if (lane < 5 && !(dbg & 2)) st.nbar[(int64_t)env * 6 + lane] = nbar_next;
@@ -723,21 +725,14 @@ __device__ __forceinline__ void fx_st_release(int32_t* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
 
-// The step kernel: one warp per env.  `chain` says how this launch depends on the kernel before it in the stream/graph
-// (all launches carry the programmatic-dependent-launch attribute, so the next kernel can be scheduled while this grid
-// drains):
-//   chain < 0   single step (fxenv_step): griddepcontrol.wait = the whole previous grid has completed and flushed.
-//   chain == 0  first step of a fxenv_step_many batch: same wait, then the env's sequence word is re-based to 0 BEFORE
-//               the dependents may launch, and set to 1 when the env-step is done.
-//   chain = j   j-th step of the batch: envs only depend on THEIR OWN previous step (the actions of the whole batch
-//               were supplied up front), so the warp waits for seq[env] == j (acquire), does the step, and publishes
-//               j + 1 (release).  The light envs of step j+1 thus run under the tail of the heavy envs of step j.
-//               No deadlock: a grid launches only after every CTA of its predecessor is resident (has executed
-//               launch_dependents), so each waiting warp waits for a warp that is already running.
-template <int STRAT, int REWARD, bool FAST5, bool CHAINED>
+// The single-step kernel: one warp per env, one env per CTA.  Launched with the programmatic-dependent-launch attribute:
+// the NEXT kernel of the stream / graph may be scheduled while this grid drains (its CTAs take SM slots as ours exit and
+// park at their own griddepcontrol.wait), which hides the launch gap between dependent steps.  Everything that touches
+// memory written by the previous kernel comes after the wait.
+template <int STRAT, int REWARD, bool FAST5>
 __global__ void __launch_bounds__(FX_WARPS * 32, FX_MIN_BLOCKS)
 fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict__ actions, float* __restrict__ obs,
-               float* __restrict__ reward, double* __restrict__ reward64, uint8_t* __restrict__ terminated, const int chain) {
+               float* __restrict__ reward, double* __restrict__ reward64, uint8_t* __restrict__ terminated) {
   extern __shared__ __align__(16) unsigned char fx_smem[];
   const FxConfig& c = P.cfg;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -746,26 +741,54 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
   const int ring_len = (REWARD == FX_REWARD_SHARPE) ? c.sharpe_window : 0;
   const int win_doubles = fx_window_doubles(c.window_size, c.n_cols);
   const WarpSmem ws = fx_carve(fx_smem + (size_t)warp * fx_warp_smem_bytes(win_doubles, ring_len), win_doubles, ring_len);
-  if (!CHAINED) {
-    asm volatile("griddepcontrol.launch_dependents;");
-    fx_window_init(lane, ws);  // mbarrier init + fence
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-  } else if (chain == 0) {
-    fx_window_init(lane, ws);
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (lane == 0) { *reinterpret_cast<volatile int32_t*>(P.seq + env) = 0; __threadfence(); }
-    __syncwarp();
-    asm volatile("griddepcontrol.launch_dependents;");
-  } else {
-    asm volatile("griddepcontrol.launch_dependents;");
-    fx_window_init(lane, ws);
-    if (lane == 0) { while (fx_ld_acquire(P.seq + env) != chain) __nanosleep(32); }
-    __syncwarp();
-  }
+  asm volatile("griddepcontrol.launch_dependents;");
+  fx_window_init(lane, ws);  // mbarrier init + fence
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   fx_step_env<STRAT, REWARD, FAST5>(P, actions, obs, reward, reward64, terminated, env, lane, ws);
-  if (CHAINED) {
+}
+
+// ---- K steps in ONE launch (fxenv_step_many): persistent warps pull (step, env) tickets ----------------------------
+// The actions of the whole batch are supplied up front, so an env only depends on ITS OWN previous step.  A grid that
+// fits the device at once keeps every warp slot busy for the whole batch: a warp takes the next ticket g from a
+// global counter (step k = g / N, env = g % N: all envs of step k are handed out before step k+1), waits until
+// seq[env] == k (acquire; the warp that finished the env's previous step released it), runs the env-step, publishes
+// seq[env] = k + 1 (release).  No kernel boundary, CTA turnaround or grid-wide barrier between steps; heavy env-steps
+// (many fills) only delay their own env.  No deadlock: the ticket an env-step waits for is lower than its own, and every
+// ticket handed out belongs to a running warp that needs nothing from higher tickets.  seq[] and the counter are zeroed
+// by a stream-ordered memset before the launch.
+template <int STRAT, int REWARD, bool FAST5>
+__global__ void __launch_bounds__(FX_WARPS * 32, FX_MIN_BLOCKS)
+fx_rollout_kernel(const __grid_constant__ FxKernelParams P, const char* __restrict__ actions, float* __restrict__ obs,
+                  const int obs_slots, float* __restrict__ reward, uint8_t* __restrict__ terminated, const int n_steps) {
+  extern __shared__ __align__(16) unsigned char fx_smem[];
+  const FxConfig& c = P.cfg;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ring_len = (REWARD == FX_REWARD_SHARPE) ? c.sharpe_window : 0;
+  const int win_doubles = fx_window_doubles(c.window_size, c.n_cols);
+  const WarpSmem ws = fx_carve(fx_smem + (size_t)warp * fx_warp_smem_bytes(win_doubles, ring_len), win_doubles, ring_len);
+  fx_window_init(lane, ws);
+  const unsigned N = (unsigned)c.num_envs;
+  const unsigned long long total = (unsigned long long)N * (unsigned)n_steps;
+  unsigned* ticket = reinterpret_cast<unsigned*>(P.seq + N);
+  unsigned g = 0u;
+  if (lane == 0) g = atomicAdd(ticket, 1u);
+  g = __shfl_sync(FX_FULL, g, 0);
+  unsigned phase = 0u;
+  while (g < total) {
+    // the ticket after this one is requested now: its atomic round trip hides behind the env-step
+    unsigned g_next = 0u;
+    if (lane == 0) g_next = atomicAdd(ticket, 1u);
+    const unsigned k = g / N, env = g - k * N;
+    if (k > 0u) {
+      if (lane == 0) { while (fx_ld_acquire(P.seq + env) != (int)k) __nanosleep(32); }
+      __syncwarp();
+    }
+    fx_step_env<STRAT, REWARD, FAST5>(P, actions + (size_t)k * N * 4, obs + (size_t)(k % (unsigned)obs_slots) * N * P.obs_dim,
+                                      reward + (size_t)k * N, nullptr, terminated + (size_t)k * N, (int)env, lane, ws, phase);
     __syncwarp();
-    if (lane == 0) fx_st_release(P.seq + (blockIdx.x * FX_WARPS + (threadIdx.x >> 5)), chain + 1);
+    if (lane == 0) fx_st_release(P.seq + env, (int)k + 1);
+    g = __shfl_sync(FX_FULL, g_next, 0);
+    phase++;
   }
 }
 
@@ -851,29 +874,43 @@ __global__ void fx_stats_kernel(FxConfig c, const double* __restrict__ candles, 
   stats[idx * 2 + 1] = rc;
 }
 
-typedef void (*StepKernel)(const FxKernelParams, const void*, float*, float*, double*, uint8_t*, int);
-
-template <int STRAT, int REWARD>
-StepKernel pick_fast(bool fast5, bool chained) {
-  if (chained) return fast5 ? fx_step_kernel<STRAT, REWARD, true, true> : fx_step_kernel<STRAT, REWARD, false, true>;
-  return fast5 ? fx_step_kernel<STRAT, REWARD, true, false> : fx_step_kernel<STRAT, REWARD, false, false>;
-}
+typedef void (*StepKernel)(const FxKernelParams, const void*, float*, float*, double*, uint8_t*);
 
 template <int STRAT>
-StepKernel pick_reward(int reward, bool fast5, bool chained) {
+StepKernel pick_reward(int reward, bool fast5) {
   switch (reward) {
-    case FX_REWARD_PNL: return pick_fast<STRAT, FX_REWARD_PNL>(fast5, chained);
-    case FX_REWARD_SHARPE: return pick_fast<STRAT, FX_REWARD_SHARPE>(fast5, chained);
-    default: return pick_fast<STRAT, FX_REWARD_DD>(fast5, chained);
+    case FX_REWARD_PNL: return fast5 ? fx_step_kernel<STRAT, FX_REWARD_PNL, true> : fx_step_kernel<STRAT, FX_REWARD_PNL, false>;
+    case FX_REWARD_SHARPE: return fast5 ? fx_step_kernel<STRAT, FX_REWARD_SHARPE, true> : fx_step_kernel<STRAT, FX_REWARD_SHARPE, false>;
+    default: return fast5 ? fx_step_kernel<STRAT, FX_REWARD_DD, true> : fx_step_kernel<STRAT, FX_REWARD_DD, false>;
   }
 }
 
-StepKernel pick_kernel(const FxKernelParams& P, bool chained) {
+StepKernel pick_kernel(const FxKernelParams& P) {
   const bool fast5 = P.fast_features == 5;
   switch (P.cfg.strategy) {
-    case FX_STRATEGY_DEFAULT: return pick_reward<FX_STRATEGY_DEFAULT>(P.cfg.reward, fast5, chained);
-    case FX_STRATEGY_FIXED_SLTP: return pick_reward<FX_STRATEGY_FIXED_SLTP>(P.cfg.reward, fast5, chained);
-    default: return pick_reward<FX_STRATEGY_ATR_SLTP>(P.cfg.reward, fast5, chained);
+    case FX_STRATEGY_DEFAULT: return pick_reward<FX_STRATEGY_DEFAULT>(P.cfg.reward, fast5);
+    case FX_STRATEGY_FIXED_SLTP: return pick_reward<FX_STRATEGY_FIXED_SLTP>(P.cfg.reward, fast5);
+    default: return pick_reward<FX_STRATEGY_ATR_SLTP>(P.cfg.reward, fast5);
+  }
+}
+
+typedef void (*RolloutKernel)(const FxKernelParams, const char*, float*, int, float*, uint8_t*, int);
+
+template <int STRAT>
+RolloutKernel pick_rollout_reward(int reward, bool fast5) {
+  switch (reward) {
+    case FX_REWARD_PNL: return fast5 ? fx_rollout_kernel<STRAT, FX_REWARD_PNL, true> : fx_rollout_kernel<STRAT, FX_REWARD_PNL, false>;
+    case FX_REWARD_SHARPE: return fast5 ? fx_rollout_kernel<STRAT, FX_REWARD_SHARPE, true> : fx_rollout_kernel<STRAT, FX_REWARD_SHARPE, false>;
+    default: return fast5 ? fx_rollout_kernel<STRAT, FX_REWARD_DD, true> : fx_rollout_kernel<STRAT, FX_REWARD_DD, false>;
+  }
+}
+
+RolloutKernel pick_rollout(const FxKernelParams& P) {
+  const bool fast5 = P.fast_features == 5;
+  switch (P.cfg.strategy) {
+    case FX_STRATEGY_DEFAULT: return pick_rollout_reward<FX_STRATEGY_DEFAULT>(P.cfg.reward, fast5);
+    case FX_STRATEGY_FIXED_SLTP: return pick_rollout_reward<FX_STRATEGY_FIXED_SLTP>(P.cfg.reward, fast5);
+    default: return pick_rollout_reward<FX_STRATEGY_ATR_SLTP>(P.cfg.reward, fast5);
   }
 }
 
@@ -889,30 +926,45 @@ size_t observe_smem_bytes(const FxKernelParams& P) {
 }  // namespace
 
 // dynamic shared memory above the 48 KB default needs an explicit opt-in per kernel
-cudaError_t fx_configure_kernels(const FxKernelParams& P) {
+cudaError_t fx_configure_kernels(FxKernelParams& P) {
   const size_t smem = step_smem_bytes(P);
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
   // ask for enough shared-memory carve-out that FX_MIN_BLOCKS CTAs (+1 KB system use each) fit on an SM
   const size_t want = (size_t)FX_MIN_BLOCKS * (smem + 1024);
   int pct = (int)((want * 100 + 228 * 1024 - 1) / (228 * 1024));
   if (pct > 100) pct = 100;
-  for (int chained = 0; chained < 2; chained++) {
-    cudaError_t e = cudaFuncSetAttribute(pick_kernel(P, chained), cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  {
+    cudaError_t e = cudaFuncSetAttribute(pick_kernel(P), cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     if (e != cudaSuccess) return e;
     if (smem > 48 * 1024) {
-      e = cudaFuncSetAttribute(pick_kernel(P, chained), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      e = cudaFuncSetAttribute(pick_kernel(P), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
     }
+  }
+  {
+    cudaError_t e = cudaFuncSetAttribute(pick_rollout(P), cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    if (e != cudaSuccess) return e;
+    if (smem > 48 * 1024) {
+      e = cudaFuncSetAttribute(pick_rollout(P), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+    }
+    // how many CTAs of the persistent rollout kernel the device holds at once (= its grid size)
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_rollout(P), FX_WARPS * 32, smem);
+    if (e != cudaSuccess) return e;
+    P.resident_blocks = sms * per_sm;
+    if (P.resident_blocks < 1) return cudaErrorInvalidConfiguration;
   }
   if (smem <= 48 * 1024) return cudaSuccess;
   return cudaFuncSetAttribute(fx_observe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)observe_smem_bytes(P));
 }
 
 cudaError_t fx_launch_step(const FxKernelParams& P, const void* actions, float* obs, float* reward, double* reward64,
-                           uint8_t* terminated, int chain, cudaStream_t stream) {
-  const int blocks = (P.cfg.num_envs + FX_WARPS - 1) / FX_WARPS;
+                           uint8_t* terminated, cudaStream_t stream) {
   cudaLaunchConfig_t lc = {};
-  lc.gridDim = dim3(blocks);
+  lc.gridDim = dim3((P.cfg.num_envs + FX_WARPS - 1) / FX_WARPS);
   lc.blockDim = dim3(FX_WARPS * 32);
   lc.dynamicSmemBytes = step_smem_bytes(P);
   lc.stream = stream;
@@ -921,8 +973,19 @@ cudaError_t fx_launch_step(const FxKernelParams& P, const void* actions, float* 
   at[0].val.programmaticStreamSerializationAllowed = 1;
   lc.attrs = at;
   lc.numAttrs = (P.debug & 4) ? 0 : 1;  // FXENV_DEBUG & 4: plain stream-serialised launches (A/B timing only)
-  if (lc.numAttrs == 0 || (P.debug & 8)) chain = -1;  // FXENV_DEBUG & 8: grid-serialised steps inside step_many (A/B timing)
-  return cudaLaunchKernelEx(&lc, pick_kernel(P, chain >= 0), P, actions, obs, reward, reward64, terminated, chain);
+  return cudaLaunchKernelEx(&lc, pick_kernel(P), P, actions, obs, reward, reward64, terminated);
+}
+
+cudaError_t fx_launch_rollout(const FxKernelParams& P, const void* actions, float* obs, int obs_slots, float* reward,
+                              uint8_t* terminated, int n_steps, cudaStream_t stream) {
+  const int N = P.cfg.num_envs;
+  cudaError_t e = cudaMemsetAsync(P.seq, 0, ((size_t)N + 1) * sizeof(int32_t), stream);
+  if (e != cudaSuccess) return e;
+  int blocks = (N + FX_WARPS - 1) / FX_WARPS;
+  if (blocks > P.resident_blocks) blocks = P.resident_blocks;
+  pick_rollout(P)<<<blocks, FX_WARPS * 32, step_smem_bytes(P), stream>>>(P, reinterpret_cast<const char*>(actions), obs, obs_slots,
+                                                                        reward, terminated, n_steps);
+  return cudaGetLastError();
 }
 
 cudaError_t fx_launch_reset(const FxKernelParams& P, const int64_t* start_bar, const uint8_t* mask, int first,

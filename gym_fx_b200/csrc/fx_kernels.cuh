@@ -45,11 +45,12 @@ struct FxKernelParams {
   FxPairTable pair[FXENV_MAX_PAIRS];
   FxDeviceState st;
   double inv_initial_cash;  // 1 / (initial_cash or 1.0)
-  int32_t* seq;             // [N] per-env sequence word of a fxenv_step_many batch (see fx_step_kernel)
+  int32_t* seq;             // [N + 1] per-env sequence words of a fxenv_step_many batch + the ticket counter (fx_rollout_kernel)
   long long* timing;        // debug (FXENV_TIMING=1): [N][FX_NSTAMP] clock64() phase stamps of the last step, else nullptr
   int32_t obs_dim;
   int32_t cap;              // logical order-table capacity (multiple of 32); arrays hold cap + FXO_SLACK
   int32_t debug;            // timing experiments only (FXENV_DEBUG): 1 skip obs windows, 2 skip broker/strategy/reward
+  int32_t resident_blocks;  // CTAs of the persistent rollout kernel resident at once on this device (SMs x occupancy)
   int32_t fast_features;    // 5: F == n_cols == 5 with identity columns (the [W][5] block is one contiguous span)
 };
 
@@ -68,9 +69,11 @@ struct FxKernelParams {
 
 // host-callable launchers (fx_kernels.cu)
 cudaError_t fx_launch_step(const FxKernelParams& P, const void* actions, float* obs, float* reward, double* reward64,
-                           uint8_t* terminated, int chain, cudaStream_t stream);
+                           uint8_t* terminated, cudaStream_t stream);
 cudaError_t fx_launch_reset(const FxKernelParams& P, const int64_t* start_bar, const uint8_t* mask, int first,
                             cudaStream_t stream);
 cudaError_t fx_launch_observe(const FxKernelParams& P, float* obs, cudaStream_t stream);
 cudaError_t fx_launch_stats(const FxConfig& cfg, const double* candles, double* stats, int64_t T, cudaStream_t stream);
-cudaError_t fx_configure_kernels(const FxKernelParams& P);
+cudaError_t fx_configure_kernels(FxKernelParams& P);
+cudaError_t fx_launch_rollout(const FxKernelParams& P, const void* actions, float* obs, int obs_slots, float* reward,
+                              uint8_t* terminated, int n_steps, cudaStream_t stream);

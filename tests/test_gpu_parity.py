@@ -258,3 +258,40 @@ def test_step_many_graph_and_step_host_match_step(cfg2_full):
     assert a_env.launch_count() >= K
     for e in (a_env, b_env, c_env):
         e.close()
+
+
+def test_step_many_rollout_kernel_matches_graph_of_steps(cfg2_full):
+    """fxenv_step_many has two engines (persistent ticket kernel / CUDA graph of single steps): same results, bit for bit,
+    over two consecutive batches with plenty of fills, and the same state snapshot afterwards."""
+    import os
+    from gym_fx_b200.vec_env import VecFxEnv
+    N, T, cfg, candles, minutes = cfg2_full
+    K = 96
+    starts = torch.as_tensor(start_offsets(N, T, 400, 256))
+    acts = torch.randint(0, 3, (2, K, N), dtype=torch.int32, generator=torch.Generator().manual_seed(11)).cuda()
+    outs = []
+    for dbg in ("16", "8"):  # 16: force the persistent launch, 8: force the graph of grid-serialised steps
+        os.environ["FXENV_DEBUG"] = dbg
+        try:
+            env = VecFxEnv(cfg, candles, minutes)
+        finally:
+            del os.environ["FXENV_DEBUG"]
+        env.reset(starts)
+        l0 = env.launch_count()
+        ring = torch.zeros((3, N, env.obs_dim), dtype=torch.float32, device="cuda")
+        rews = torch.zeros((2, K, N), dtype=torch.float32, device="cuda")
+        terms = torch.zeros((2, K, N), dtype=torch.uint8, device="cuda")
+        for b in range(2):
+            env.step_many(acts[b], ring, rews[b], terms[b])
+        torch.cuda.synchronize()
+        inf = env.info()
+        info = {k: inf[k].clone() for k in ("equity", "position", "price", "bar_index", "trades", "commission_paid")}
+        outs.append((ring, rews, terms, info, env.get_state(), env.launch_count() - l0))
+        env.close()
+    a, b = outs
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+    for k in a[3]:
+        assert torch.equal(a[3][k], b[3][k]), k
+    assert bytes(a[4]) == bytes(b[4])
+    assert a[5] == 2 and b[5] == 2 * K  # one launch per batch vs one per step
+    assert float(a[3]["trades"].float().mean()) > 5.0  # the batches really traded
