@@ -5,13 +5,16 @@ bench.py -- env-steps/sec of the gym-fx env.step() hot path (BASELINE.json metri
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3|cfg4|cfg5]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" = one env.step() of every env of the workload (one launch of the fused kernel per GPU).  Default
+A "step" = one env.step() of every env of the workload.  Default
 workload = BASELINE configs[1]: 4096 envs/GPU, feature_window_preprocessor (window=128, 5 OHLCV features, rolling
 z-score over 256 bars), direct_fixed_sltp, pnl_reward, synthetic EURUSD 1-min candles (2^19 bars).
 
-ours:       K steps as one CUDA-graph replay of K kernel launches (fxenv_step_many), actions pre-generated on the
-            device, observation rows rotating through a ring LARGER than L2 so every step's stores reach HBM.
+ours:       K steps through fxenv_step_many in batches of <= 500 (actions pre-generated on the device, observation rows
+            rotating through a ring LARGER than L2 so every step's stores reach HBM).  The library runs a batch either
+            as ONE persistent launch whose warps pull (step, env) tickets and honour per-env dependencies, or as a CUDA
+            graph of single-step launches (include/fxenv.h: fxenv_step_many_engine) -- `config.engine` says which.
             `value` = whole-job env-steps/s (inputs resident in HBM), max-over-ranks device time.
+            `single_step_graph` = the same K steps forced through the graph of grid-serialised single steps.
             `e2e`   = same metric through the reference-facing host-buffer call (fxenv_step_host): per step H2D of
             the actions from pinned memory, the kernel, D2H of obs/reward/terminated, host sync.
             `roofline` = algorithmic bytes per launch / average launch duration vs measured HBM peak.
@@ -171,6 +174,35 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def single_step_graph_rate(args, cfg, candles, minutes, N, starts, acts, ring, rews, terms, chunk):
+    """The same steps through the other fxenv_step_many engine (CUDA graph of grid-serialised single-step launches),
+    which is also what a policy-in-the-loop caller of fxenv_step gets: reported next to `value` for transparency."""
+    import torch
+    from gym_fx_b200.vec_env import VecFxEnv
+
+    os.environ["FXENV_DEBUG"] = "8"
+    try:
+        env = VecFxEnv(cfg, candles, minutes, device=ring.device)
+    finally:
+        del os.environ["FXENV_DEBUG"]
+    env.reset(starts)
+    K = min(args.steps, 2 * chunk)
+    reps = max(1, K // chunk)
+    for _ in range(2):
+        env.step_many(acts, ring, rews, terms)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(reps):
+        env.step_many(acts, ring, rews, terms)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    env.close()
+    return {"value": N * reps * chunk / (ms * 1e-3), "unit": "env-steps/s", "ms_per_step": ms / (reps * chunk), "steps": reps * chunk,
+            "note": "CUDA graph of single-step launches (grid-wide dependency between steps, programmatic dependent launch)"}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     from gym_fx_b200.sharding import check_pair_alignment, shard_starts
@@ -229,6 +261,7 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
     clocks = sampler.stop() if sampler else None
+    engine = env.step_many_engine(chunk)
     overflow = int((env.info()["flags"] & 16).ne(0).sum().item())
     term_frac = float(terms.float().mean().item())
 
@@ -263,7 +296,8 @@ def run_ours(args, rank, world, local_rank):
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-                traffic = json.load(fh).get(args.workload)
+                per_step = json.load(fh).get(args.workload + "_per_step")
+                traffic = per_step * (K // max(1, int(launches))) if per_step and args.envs is None else None
         except Exception:
             pass
         line = {
@@ -273,7 +307,9 @@ def run_ours(args, rank, world, local_rank):
             "config": {"workload": desc, "envs_per_gpu": N, "obs_dim": D, "parallelism": f"env-shard x{world}",
                        "actions": "uniform {0,1,2}, torch.Generator(seed=1234+rank), pre-generated on device",
                        "l2": f"obs rows rotate through a {slots}-slot ring ({slots * N * D * 4 / 2**20:.0f} MiB > 126 MiB L2)",
-                       "graph": f"{chunk} step kernels per CUDA-graph replay", "order_overflow_envs": overflow,
+                       "engine": (f"persistent launch: {chunk} steps per launch, warps pull (step, env) tickets, per-env dependencies"
+                                  if engine == "persistent" else f"CUDA graph of {chunk} single-step launches (programmatic dependent launch)"),
+                       "order_overflow_envs": overflow,
                        "terminated_frac": term_frac},
             "clocks": clocks,
             "e2e": {"value": e2e_rate, "unit": "env-steps/s", "h2d_bytes_per_step": N * 4,
@@ -281,10 +317,15 @@ def run_ours(args, rank, world, local_rank):
                     "note": "fxenv_step_host: pinned host buffers, synchronous per step (PCIe-bound)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "fx_step_kernel",
-                         "algorithmic_bytes_per_launch": N * algo_bytes,
-                         "avg_launch_us": per_launch_s * 1e6},
+                         "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "fx_rollout_kernel" if engine == "persistent" else "fx_step_kernel",
+                         "algorithmic_bytes_per_launch": N * algo_bytes * (K // max(1, int(launches))),
+                         "avg_launch_us": ms_max * 1e3 / max(1, int(launches)),
+                         "note": "achieved = algorithmic bytes of the timed region / its CUDA-event duration (the "
+                                 "region is back-to-back launches of this one kernel); traffic = ncu dram bytes per env-step x envs"},
         }
+        if world == 1 and engine == "persistent" and not args.no_single_step:
+            line["single_step_graph"] = single_step_graph_rate(args, cfg, candles, minutes, N, starts, acts, ring, rews, terms, chunk)
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             sample_envs = min(N, 4096)
@@ -307,6 +348,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--envs", type=int, default=None, help="envs per GPU (default: the workload's)")
+    ap.add_argument("--no-single-step", action="store_true", help="skip the single-step-graph reference measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -18,7 +18,7 @@ CSRC = os.path.join(_HERE, "csrc")
 EXPORTS = [
     "fxenv_abi_version", "fxenv_create", "fxenv_destroy", "fxenv_last_error", "fxenv_load_candles", "fxenv_obs_dim",
     "fxenv_reset", "fxenv_observe", "fxenv_step", "fxenv_step_many", "fxenv_step_host", "fxenv_get_info",
-    "fxenv_state_bytes", "fxenv_get_state", "fxenv_set_state", "fxenv_launch_count",
+    "fxenv_state_bytes", "fxenv_get_state", "fxenv_set_state", "fxenv_launch_count", "fxenv_step_many_engine",
 ]
 
 
@@ -87,6 +87,8 @@ def load():
     L.fxenv_set_state.argtypes = [vp, vp, i64]
     L.fxenv_launch_count.restype = i64
     L.fxenv_launch_count.argtypes = [vp]
+    L.fxenv_step_many_engine.restype = C.c_int
+    L.fxenv_step_many_engine.argtypes = [vp, C.c_int]
     if L.fxenv_abi_version() != 1:
         raise FxEnvError("libfxenv.so ABI version mismatch")
     _lib = L

@@ -299,6 +299,18 @@ int fxenv_step(FxEnv* env, const void* actions_dev, float* obs_dev, float* rewar
   return FXENV_OK;
 }
 
+static bool batch_uses_rollout(const FxEnv* env, int n_steps) {
+  bool rollout = n_steps > 1 && (long long)env->P.cfg.num_envs <= 3ll * env->P.resident_blocks * FX_WARPS;
+  if (env->P.debug & (4 | 8)) rollout = false;             // FXENV_DEBUG: force the graph of single steps (A/B timing)
+  if ((env->P.debug & 16) && n_steps > 1) rollout = true;  // FXENV_DEBUG & 16: force the persistent launch
+  return rollout;
+}
+
+int fxenv_step_many_engine(const FxEnv* env, int n_steps) {
+  if (!env) return FXENV_E_INVALID;
+  return batch_uses_rollout(env, n_steps) ? 1 : 0;
+}
+
 int fxenv_step_many(FxEnv* env, int n_steps, const void* actions_dev, float* obs_dev, int obs_slots, float* reward_dev,
                     uint8_t* terminated_dev, void* stream_) {
   int rc = require_ready(env, true);
@@ -322,9 +334,7 @@ int fxenv_step_many(FxEnv* env, int n_steps, const void* actions_dev, float* obs
   // step (envs with many fills) overlaps the next step; (b) a CUDA graph of K single-step launches -- wins once the
   // device is saturated anyway (measured on B200: cfg2/cfg4 4096 envs (a) 13.3 / 17.4 vs (b) 20.0 / 24.5 us per step;
   // cfg3 16384 envs (a) 81.9 vs (b) 70.2; cfg5 8192 envs W=512 (a) 75.4 vs (b) 74.1).
-  bool rollout = n_steps > 1 && (long long)N <= 3ll * env->P.resident_blocks * FX_WARPS;
-  if (env->P.debug & (4 | 8)) rollout = false;        // FXENV_DEBUG: force the graph of single steps (A/B timing)
-  if ((env->P.debug & 16) && n_steps > 1) rollout = true;  // FXENV_DEBUG & 16: force the persistent launch
+  const bool rollout = batch_uses_rollout(env, n_steps);
   if (rollout) {
     if ((unsigned long long)N * (unsigned long long)n_steps >= (1ull << 31))
       return fail(env, FXENV_E_INVALID, "num_envs * n_steps must be < 2^31 per fxenv_step_many call");

@@ -146,6 +146,10 @@ class VecFxEnv:
     def launch_count(self) -> int:
         return int(self.L.fxenv_launch_count(self._h))
 
+    def step_many_engine(self, n_steps: int) -> str:
+        """'persistent' (one launch, per-env dependencies) or 'graph' (CUDA graph of single steps) -- see fxenv.h."""
+        return "persistent" if int(self.L.fxenv_step_many_engine(self._h, int(n_steps))) == 1 else "graph"
+
     def get_state(self) -> bytes:
         n = self.L.fxenv_state_bytes(self._h)
         buf = (C.c_char * n)()

@@ -175,11 +175,17 @@ int fxenv_observe(FxEnv* env, float* obs_dev, void* stream);
 int fxenv_step(FxEnv* env, const void* actions_dev, float* obs_dev, float* reward_dev, uint8_t* terminated_dev,
                double* reward64_dev, void* stream);
 
-/* n_steps consecutive steps; step k reads actions_dev + k*num_envs and writes reward/terminated at k*num_envs;
- * obs rows go to obs_dev + (k % obs_slots)*num_envs*obs_dim (obs_slots >= 1).  The launch sequence is cached
- * as a CUDA graph keyed by the pointer set. */
+/* n_steps consecutive steps with the actions of the whole batch supplied up front (replayed / random / scripted
+ * drivers: strategy_plugins/default_strategy.py:38-53, the loop of app/main.py:57-65); step k reads
+ * actions_dev + k*num_envs and writes reward/terminated at k*num_envs; obs rows go to
+ * obs_dev + (k % obs_slots)*num_envs*obs_dim (obs_slots >= 1).  Results are identical to n_steps calls of fxenv_step.
+ * Two engines, chosen by size (fxenv_step_many_engine): 1 = one persistent launch whose warps pull (step, env) tickets
+ * and honour per-env dependencies only; 0 = a CUDA graph of n_steps single-step launches, cached by pointer set. */
 int fxenv_step_many(FxEnv* env, int n_steps, const void* actions_dev, float* obs_dev, int obs_slots,
                     float* reward_dev, uint8_t* terminated_dev, void* stream);
+
+/* Which engine fxenv_step_many would use for a batch of n_steps (1 persistent launch / 0 graph of steps), <0 on error. */
+int fxenv_step_many_engine(const FxEnv* env, int n_steps);
 
 /* Reference-facing call with HOST buffers: H2D actions, one step, D2H obs/reward/terminated, then waits. */
 int fxenv_step_host(FxEnv* env, const void* actions_host, float* obs_host, float* reward_host,

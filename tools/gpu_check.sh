@@ -13,9 +13,11 @@ tests) timeout 900 python -m pytest tests -m gpu -q -p no:cacheprovider --timeou
 bench) for wl in cfg2 cfg3 cfg4 cfg5; do
          timeout 300 python bench.py --workload $wl --steps 1000 --warmup 100 > $OUT/bench_$wl.json 2> $OUT/bench_$wl.err; echo "bench $wl rc=$?"; tail -c 1500 $OUT/bench_$wl.json; done
        timeout 300 python bench.py --impl reference --steps 200 --warmup 5 > $OUT/bench_ref.json 2> $OUT/bench_ref.err; tail -c 600 $OUT/bench_ref.json ;;
-ncu)   timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 320 -c 100 --csv --log-file $OUT/launches.csv \
-         python bench.py --steps 100 --warmup 300 --no-cpu-baseline > $OUT/ncu_launch.log 2>&1; echo "ncu launches rc=$?"
-       timeout 600 ncu --set full --clock-control none --import-source on -k regex:fx_step -s 340 -c 2 -f -o $OUT/prof_step \
-         python bench.py --steps 100 --warmup 300 --no-cpu-baseline > $OUT/ncu_full.log 2>&1; echo "ncu full rc=$?" ;;
+ncu)   timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
+         python bench.py --steps 1000 --warmup 500 --no-cpu-baseline --no-single-step > $OUT/ncu_launch.log 2>&1; echo "ncu launches rc=$?"
+       timeout 600 ncu --set full --clock-control none --import-source on -k regex:fx_rollout -s 1 -c 1 -f -o $OUT/prof_rollout \
+         python bench.py --steps 200 --warmup 100 --no-cpu-baseline --no-single-step > $OUT/ncu_full.log 2>&1; echo "ncu full rc=$?"
+       FXENV_DEBUG=8 timeout 600 ncu --set full --clock-control none --import-source on -k regex:fx_step -s 340 -c 1 -f -o $OUT/prof_step \
+         python bench.py --steps 100 --warmup 300 --no-cpu-baseline --no-single-step > $OUT/ncu_full2.log 2>&1; echo "ncu full (single step) rc=$?" ;;
 esac; done
 ls -la $OUT
