@@ -127,4 +127,31 @@ void hs_info(HsEnv* h, double* d7, int32_t* i5, uint32_t* flags) {
   *flags = e.flags;
 }
 
+// Cross-check of the two forms of the trigger test the kernel uses: fx_entry_fill (select form, also returns the
+// execution price; what the CUDA kernel evaluates per lane) against fx_entry_hits + the branchy fx_match_* rules (what
+// fx_exec_entry uses).  Random entries / bars, including bars whose OPEN lies outside [LOW, HIGH] and exact ties.
+// Returns the number of disagreements.
+int hs_check_entry_fill(int n, unsigned seed) {
+  unsigned long long x = 0x9E3779B97F4A7C15ull ^ seed;
+  auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+  auto price = [&]() { return 1.0 + (double)(rnd() % 41) * 0.0005; };  // coarse grid => many exact ties
+  int bad = 0;
+  for (int i = 0; i < n; i++) {
+    FxBar b{price(), price(), price(), price()};
+    const uint32_t kind = (uint32_t)(rnd() % 3);
+    const uint32_t meta = kind | ((rnd() & 1) ? FXO_SELL : 0u) | ((rnd() & 1) ? FXO_ACTIVE : 0u);
+    const double p0 = price(), p1 = price();
+    double px = -1.0;
+    const bool hit = fx_entry_fill(meta, p0, p1, b, px);
+    const bool buy = !(meta & FXO_SELL);
+    double ref_px = b.o;
+    bool ref;
+    if (kind == FXO_MARKET) ref = true;
+    else if (kind == FXO_PARENT) ref = fx_match_limit(buy, p0, b, ref_px);
+    else ref = fx_match_stop(buy, p0, b, ref_px) || fx_match_limit(buy, p1, b, ref_px);
+    if (hit != ref || hit != fx_entry_hits(meta, p0, p1, b) || (hit && px != ref_px)) bad++;
+  }
+  return bad;
+}
+
 }  // extern "C"

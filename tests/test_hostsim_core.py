@@ -32,3 +32,14 @@ def test_core_matches_golden(name):
         if has_agent and k in rows:
             np.testing.assert_allclose(env.scalars(), g["obs"][rows[k], lay_scal:], rtol=1e-6, atol=1e-7,
                                        err_msg=f"{name} agent scalars row {k}")
+
+
+def test_entry_fill_select_form_matches_branchy_rules():
+    """fx_entry_fill (what every lane of the CUDA kernel evaluates) == fx_entry_hits + fx_match_limit / fx_match_stop."""
+    import ctypes as C
+    from hostsim.hostsim import lib
+    L = lib()
+    L.hs_check_entry_fill.argtypes = [C.c_int, C.c_uint]
+    L.hs_check_entry_fill.restype = C.c_int
+    for seed in (1, 2, 3):
+        assert L.hs_check_entry_fill(200000, seed) == 0
