@@ -35,6 +35,7 @@ struct FxEnv {
   double* stats_dev[FXENV_MAX_PAIRS] = {};
   int64_t* minutes_dev[FXENV_MAX_PAIRS] = {};
   bool loaded[FXENV_MAX_PAIRS] = {};
+  bool tame[FXENV_MAX_PAIRS] = {};
   bool was_reset = false;
   bool first_reset = true;
   int64_t launches = 0;
@@ -261,6 +262,12 @@ int fxenv_load_candles(FxEnv* env, int pair_id, const double* candles_host, int6
   tb.minutes = env->minutes_dev[pair_id];
   tb.T = T;
   env->loaded[pair_id] = true;
+  // finite and far from overflow => the observation code may skip its NaN fix-up (FxKernelParams::tame_data)
+  bool tame = true;
+  for (size_t i = 0, n = (size_t)T * c.n_cols; i < n && tame; i++) tame = fabs(candles_host[i]) < 1e100;  // false for NaN / inf
+  env->tame[pair_id] = tame;
+  env->P.tame_data = 1;
+  for (int p = 0; p < c.num_pairs; p++) if (env->loaded[p] && !env->tame[p]) env->P.tame_data = 0;
   return FXENV_OK;
 }
 

@@ -165,14 +165,16 @@ __device__ __forceinline__ bool fx_prepare_stats(const FxKernelParams& P, const 
 // ---- observation windows: preprocessor.make_observation (features | prices | returns) in the flat VecEnv layout ----
 // `win` = the staged rows [left, s) (shift already applied): element (k, col) at win[k * C + col].
 // float32 finishing of one feature value: np.clip then np.nan_to_num (feature_window_preprocessor.py:119-123)
-template <bool CLIP>
+// TAME: every table value is finite and below 1e100 in magnitude (checked at fxenv_load_candles), so a z-score can
+// overflow to +-inf but never be NaN and the nan -> 0 fix-up is dead code.
+template <bool CLIP, bool TAME>
 __device__ __forceinline__ float fx_finish_t(float v, float clipf) {
-  v = (v != v) ? 0.0f : v;
+  if (!TAME) v = (v != v) ? 0.0f : v;
   if (CLIP) return fminf(fmaxf(v, -clipf), clipf);  // also maps +-inf to +-clip
   return isinf(v) ? (v > 0.0f ? clipf : -clipf) : v;
 }
 
-template <bool FAST5, bool CLIP>
+template <bool FAST5, bool CLIP, bool TAME>
 __device__ __noinline__ void fx_emit_windows_t(const FxKernelParams& P, int lane, int s, bool scale,
                                                const double* __restrict__ win, const double* sstat,
                                                float* __restrict__ out) {
@@ -200,15 +202,15 @@ __device__ __noinline__ void fx_emit_windows_t(const FxKernelParams& P, int lane
         for (int q = lane; q < npair; q += 30) {
           const double x0 = win[2 * q], x1 = win[2 * q + 1];
           float2 v;
-          v.x = fx_finish_t<CLIP>((float)((x0 - m0) * r0), clipf);
-          v.y = fx_finish_t<CLIP>((float)((x1 - m1) * r1), clipf);
+          v.x = fx_finish_t<CLIP, TAME>((float)((x0 - m0) * r0), clipf);
+          v.y = fx_finish_t<CLIP, TAME>((float)((x1 - m1) * r1), clipf);
           __stcs(reinterpret_cast<float2*>(out) + q, v);
         }
         if ((total & 1) && lane == 0) {
           const int j = total - 1, f = j % 5;
           const bool z = scale && !c.feature_binary[f];
           const double x = win[j];
-          __stcs(out + j, fx_finish_t<CLIP>(z ? (float)((x - sstat[2 * f]) * sstat[2 * f + 1]) : (float)x, clipf));
+          __stcs(out + j, fx_finish_t<CLIP, TAME>(z ? (float)((x - sstat[2 * f]) * sstat[2 * f + 1]) : (float)x, clipf));
         }
       }
     } else {
@@ -220,7 +222,7 @@ __device__ __noinline__ void fx_emit_windows_t(const FxKernelParams& P, int lane
         if (k < 0) k = 0;
         const double x = win[k * C + c.feature_cols[f]];
         const float v = (scale && !c.feature_binary[f]) ? (float)((x - sstat[2 * f]) * sstat[2 * f + 1]) : (float)x;
-        __stcs(out + j, fx_finish_t<CLIP>(v, clipf));
+        __stcs(out + j, fx_finish_t<CLIP, TAME>(v, clipf));
         w += dw; f += df;
         if (f >= F) { f -= F; w += 1; }
       }
@@ -249,8 +251,12 @@ template <bool FAST5>
 __device__ __forceinline__ void fx_emit_windows(const FxKernelParams& P, int lane, int s, bool scale,
                                                 const double* __restrict__ win, const double* sstat,
                                                 float* __restrict__ out) {
-  if (P.cfg.feature_clip > 0.0) fx_emit_windows_t<FAST5, true>(P, lane, s, scale, win, sstat, out);
-  else fx_emit_windows_t<FAST5, false>(P, lane, s, scale, win, sstat, out);
+  if (P.cfg.feature_clip > 0.0) {
+    if (P.tame_data) fx_emit_windows_t<FAST5, true, true>(P, lane, s, scale, win, sstat, out);
+    else fx_emit_windows_t<FAST5, true, false>(P, lane, s, scale, win, sstat, out);
+  } else {
+    fx_emit_windows_t<FAST5, false, false>(P, lane, s, scale, win, sstat, out);
+  }
 }
 
 // issue + wait + emit in one go (terminated path, observe kernel)

@@ -51,6 +51,7 @@ struct FxKernelParams {
   int32_t cap;              // logical order-table capacity (multiple of 32); arrays hold cap + FXO_SLACK
   int32_t debug;            // timing experiments only (FXENV_DEBUG): 1 skip obs windows, 2 skip broker/strategy/reward
   int32_t resident_blocks;  // CTAs of the persistent rollout kernel resident at once on this device (SMs x occupancy)
+  int32_t tame_data;        // 1: every loaded table value is finite and |x| < 1e100 (no NaN can arise in a z-score)
   int32_t fast_features;    // 5: F == n_cols == 5 with identity columns (the [W][5] block is one contiguous span)
 };
 

@@ -295,3 +295,29 @@ def test_step_many_rollout_kernel_matches_graph_of_steps(cfg2_full):
     assert bytes(a[4]) == bytes(b[4])
     assert a[5] == 2 and b[5] == 2 * K  # one launch per batch vs one per step
     assert float(a[3]["trades"].float().mean()) > 5.0  # the batches really traded
+
+
+def test_gpu_nan_inf_feature_values_follow_nan_to_num():
+    """Untamed tables (NaN / +-inf in a feature column) take the general observation path: np.clip then np.nan_to_num
+    (feature_window_preprocessor.py:119-123) -- NaN -> 0, +-inf -> +-clip -- exactly like the oracle."""
+    N, T, steps = 64, 3000, 120
+    cols = list(S.OHLCV) + ["FEAT_A"]
+    cfgd = dict(window_size=16, feature_columns=["CLOSE", "VOLUME", "FEAT_A"], feature_scaling_window=32)
+    cfg, candles, minutes = _mk(cfgd, dict(strategy="direct_fixed_sltp", preprocessor="feature_window_preprocessor"), N, T=T,
+                                columns=cols, order_capacity=256)
+    rng = np.random.default_rng(5)
+    extra = rng.normal(0.0, 1.0, T)
+    extra[rng.integers(0, T, 60)] = np.nan
+    extra[rng.integers(0, T, 30)] = np.inf
+    extra[rng.integers(0, T, 30)] = -np.inf
+    candles = [np.ascontiguousarray(np.concatenate([candles[0], extra[:, None]], axis=1))]
+    starts = start_offsets(N, T, steps + 10, 40)
+    gpu, orc = GpuVec(cfg, candles, minutes), OracleVec(cfg, candles, minutes)
+    go, oo = gpu.reset(starts), orc.reset(starts)
+    assert np.array_equal(np.isfinite(go), np.isfinite(oo)) and np.all(np.isfinite(go))
+    for k in range(steps):
+        a = rng.integers(0, 3, N).astype(np.int32)
+        g, o = gpu.step(a), orc.step(a)
+        assert np.all(np.isfinite(g[0]))
+        compare_step(f"nan/inf step {k}", g, o)
+    gpu.close()
