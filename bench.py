@@ -171,7 +171,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": rate, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_json(line)
 
 
 def single_step_graph_rate(args, cfg, candles, minutes, N, starts, acts, ring, rews, terms, chunk):
@@ -333,14 +333,36 @@ def run_ours(args, rank, world, local_rank):
             line["cpu_baseline"] = {"value": rate, "unit": "env-steps/s", "cores": used, "kind": "port",
                                     "sample": f"{sample_envs} envs x {done} steps ({dt:.1f} s), C oracle port, {used} host threads, "
                                               f"no per-step barrier"}
-        print(json.dumps(line), flush=True)
+        emit_json(line)
     env.close()
     if dist:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Library chatter (e.g. NCCL's version banner) must not land on stdout: the contract is ONE JSON line there."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_json(line):
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(line), flush=True)
+    if _REAL_STDOUT is not None:
+        os.dup2(2, 1)
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2000)
