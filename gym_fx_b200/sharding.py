@@ -38,3 +38,39 @@ def max_over_ranks(value: float, dist=None, device=None) -> float:
     t = torch.tensor([float(value)], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+# ---- learner-side collectives: only a PPO learner built on top of the env needs these; the step path has none
+
+def allreduce_mean_grads(params, dist=None, group=None) -> None:
+    """Average the gradients of `params` across ranks with ONE all-reduce of a flat bucket (the policy is tiny --
+    ~0.3 M parameters -- so the collective is latency-bound: one bucket, not one call per tensor)."""
+    if dist is None or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    import torch
+
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat.div_(dist.get_world_size(group))
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g))
+        off += n
+
+
+def global_mean_std(x, dist=None, group=None, eps: float = 1e-8):
+    """Mean / std of `x` over ALL ranks' elements from one all-reduce of [sum, sum of squares, count] (advantage
+    normalisation of a sharded rollout).  Returns (mean, std) as 0-d tensors on x's device."""
+    import torch
+
+    x64 = x.reshape(-1).to(torch.float64)
+    s = torch.stack([x64.sum(), (x64 * x64).sum(), torch.tensor(float(x64.numel()), dtype=torch.float64, device=x.device)])
+    if dist is not None and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(s, op=dist.ReduceOp.SUM, group=group)
+    mean = s[0] / s[2]
+    var = torch.clamp(s[1] / s[2] - mean * mean, min=0.0)
+    return mean.to(x.dtype), torch.sqrt(var).to(x.dtype) + eps

@@ -107,3 +107,48 @@ def test_shard_helpers():
         check_pair_alignment(6, 4)
     with pytest.raises(ValueError):
         shard_range(4, 2, 2)
+
+
+def _learner_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path[:0] = [ROOT]
+    from gym_fx_b200.sharding import allreduce_mean_grads, global_mean_std
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 2))
+    g = torch.Generator().manual_seed(100)
+    x_all = torch.randn(8, 6, generator=g)
+    adv_all = torch.randn(40, generator=g) * 3 + 1
+    x = x_all[rank * 4:(rank + 1) * 4]
+    net(x).pow(2).mean().backward()                 # local minibatch = this rank's shard
+    allreduce_mean_grads(list(net.parameters()), dist)
+    grads = torch.cat([p.grad.reshape(-1) for p in net.parameters()])
+    m, s = global_mean_std(adv_all[rank * 20:(rank + 1) * 20], dist)
+    q.put((rank, grads.numpy(), float(m), float(s)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_learner_collectives_world2_match_single_process():
+    """allreduce_mean_grads / global_mean_std over two gloo ranks == the single-process result over the whole batch."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_learner_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=120) for _ in range(2)), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 2))
+    g = torch.Generator().manual_seed(100)
+    x_all = torch.randn(8, 6, generator=g)
+    adv_all = torch.randn(40, generator=g) * 3 + 1
+    net(x_all).pow(2).mean().backward()             # equal shard sizes: mean of shard means == global mean
+    ref = torch.cat([p.grad.reshape(-1) for p in net.parameters()]).numpy()
+    for _, grads, m, s in res:
+        np.testing.assert_allclose(grads, ref, rtol=1e-5, atol=1e-7)
+        assert abs(m - float(adv_all.mean())) < 1e-5 and abs(s - float(adv_all.std(unbiased=False))) < 1e-5
