@@ -91,7 +91,7 @@ int validate(const FxConfig& c, std::string& why) {
   if (c.order_capacity < 0 || c.order_capacity > 512) BAD("order_capacity must be in 0..512");
   if (c.window_size < 1) BAD("window_size must be >= 1");
   if (c.price_col < 0 || c.price_col >= c.n_cols) BAD("price_col out of range");
-  if (c.slippage_perc != 0.0) BAD("slippage_perc != 0 is not supported yet");
+  if (!(c.slippage_perc >= 0.0 && c.slippage_perc < 1.0)) BAD("slippage_perc must be in [0, 1)");
   if (!(c.leverage > 0.0)) BAD("leverage must be > 0");
   if (c.strategy < 0 || c.strategy > FX_STRATEGY_ATR_SLTP) BAD("unknown strategy %d", c.strategy);
   if (c.strategy == FX_STRATEGY_ATR_SLTP && (c.atr_period < 1 || c.atr_period > 64)) BAD("atr_period must be in 1..64");

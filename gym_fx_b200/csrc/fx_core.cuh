@@ -173,25 +173,43 @@ FX_HD bool fx_execute(const FxConfig& c, FxEnvRegs& e, double size, double price
   return margin;
 }
 
-// ---- matching rules (bbroker.py _try_exec_market / _try_exec_limit / _try_exec_stop), no slippage --------------
-FX_HD bool fx_match_limit(bool buy, double plimit, const FxBar& b, double& px) {
+// ---- matching rules (bbroker.py _try_exec_market / _try_exec_limit / _try_exec_stop) -----------------------------
+// Slippage: BackBroker._slip_up / _slip_down as configured by the reference (set_slippage_perc(perc, slip_open=True,
+// slip_limit=True, slip_match=True), slip_out=False -- broker_plugins/default_broker.py:50-51): the slipped price,
+// capped at the bar's extreme.  perc == 0 must bypass the cap (bars whose OPEN lies outside [LOW, HIGH] exist).
+FX_HD double fx_slip_up(double s, double pmax, double price) {
+  if (s == 0.0) return price;
+  const double pslip = price * (1 + s);
+  return pslip <= pmax ? pslip : pmax;
+}
+FX_HD double fx_slip_down(double s, double pmin, double price) {
+  if (s == 0.0) return price;
+  const double pslip = price * (1 - s);
+  return pslip >= pmin ? pslip : pmin;
+}
+
+FX_HD double fx_market_price(double s, bool buy, const FxBar& b) {
+  return buy ? fx_slip_up(s, b.h, b.o) : fx_slip_down(s, b.l, b.o);
+}
+
+FX_HD bool fx_match_limit(double s, bool buy, double plimit, const FxBar& b, double& px) {
   if (buy) {
-    if (plimit >= b.o) { px = b.o; return true; }
+    if (plimit >= b.o) { px = fx_slip_up(s, b.h < plimit ? b.h : plimit, b.o); return true; }
     if (plimit >= b.l) { px = plimit; return true; }
   } else {
-    if (plimit <= b.o) { px = b.o; return true; }
+    if (plimit <= b.o) { px = fx_slip_down(s, plimit, b.o); return true; }  // bbroker passes plimit, not max(low, plimit)
     if (plimit <= b.h) { px = plimit; return true; }
   }
   return false;
 }
 
-FX_HD bool fx_match_stop(bool buy, double pstop, const FxBar& b, double& px) {
+FX_HD bool fx_match_stop(double s, bool buy, double pstop, const FxBar& b, double& px) {
   if (buy) {
-    if (b.o >= pstop) { px = b.o; return true; }
-    if (b.h >= pstop) { px = pstop; return true; }
+    if (b.o >= pstop) { px = fx_slip_up(s, b.h, b.o); return true; }
+    if (b.h >= pstop) { px = fx_slip_up(s, b.h, pstop); return true; }
   } else {
-    if (b.o <= pstop) { px = b.o; return true; }
-    if (b.l <= pstop) { px = pstop; return true; }
+    if (b.o <= pstop) { px = fx_slip_down(s, b.l, b.o); return true; }
+    if (b.l <= pstop) { px = fx_slip_down(s, b.l, pstop); return true; }
   }
   return false;
 }
@@ -203,13 +221,13 @@ FX_HD bool fx_entry_hits(uint32_t meta, double p0, double p1, const FxBar& b) {
   const bool buy = !(meta & FXO_SELL);
   double px;
   if (kind == FXO_MARKET) return true;
-  if (kind == FXO_PARENT) return fx_match_limit(buy, p0, b, px);
-  return fx_match_stop(buy, p0, b, px) || fx_match_limit(buy, p1, b, px);
+  if (kind == FXO_PARENT) return fx_match_limit(0.0, buy, p0, b, px);
+  return fx_match_stop(0.0, buy, p0, b, px) || fx_match_limit(0.0, buy, p1, b, px);
 }
 
 // Same test, also returning the execution price (select form: every lane of a warp evaluates it without divergence).
 // The price is a pure function of (entry, bar) as well, so the FIFO walk only has to fetch it from the owning lane.
-FX_HD bool fx_entry_fill(uint32_t meta, double p0, double p1, const FxBar& b, double& px) {
+FX_HD bool fx_entry_fill(double s, uint32_t meta, double p0, double p1, const FxBar& b, double& px) {
   const uint32_t kind = meta & FXO_KIND_MASK;
   const bool buy = !(meta & FXO_SELL);
   // stop @p0 (PAIR) -- bbroker.py _try_exec_stop
@@ -219,11 +237,15 @@ FX_HD bool fx_entry_fill(uint32_t meta, double p0, double p1, const FxBar& b, do
   const double pl = (kind == FXO_PARENT) ? p0 : p1;
   const bool l_open = buy ? (pl >= b.o) : (pl <= b.o);
   const bool l_hit = l_open || (buy ? (pl >= b.l) : (pl <= b.h));
-  if (kind == FXO_MARKET) { px = b.o; return true; }
-  if (kind == FXO_PARENT) { px = l_open ? b.o : pl; return l_hit; }
-  if (s_hit) { px = s_open ? b.o : p0; return true; }  // the stop leg is tried first
-  px = l_open ? b.o : pl;
-  return l_hit;
+  bool hit;
+  double base, cap;  // un-slipped price and the bound the slipped price is capped at
+  bool slips = true;
+  if (kind == FXO_MARKET) { hit = true; base = b.o; cap = buy ? b.h : b.l; }
+  else if (kind == FXO_PAIR && s_hit) { hit = true; base = s_open ? b.o : p0; cap = buy ? b.h : b.l; }
+  else { hit = l_hit; base = l_open ? b.o : pl; slips = l_open; cap = buy ? (b.h < pl ? b.h : pl) : pl; }
+  px = base;
+  if (s != 0.0 && slips) px = buy ? fx_slip_up(s, cap, base) : fx_slip_down(s, cap, base);
+  return hit;
 }
 
 // ---- BackBroker.next, step 0: "while self._toactivate: activate()" -- per entry, lane-parallel on the device ------
@@ -279,11 +301,12 @@ FX_HD void fx_exec_entry(const FxConfig& c, FxEnvRegs& e, FxOrderTab& t, int k, 
   if (m & (FXO_DEAD | FXO_SUBMITTED)) return;
   const uint32_t kind = m & FXO_KIND_MASK;
   const bool buy = !(m & FXO_SELL);
+  const double s = c.slippage_perc;
   double px = b.o;
   bool go;
-  if (kind == FXO_MARKET) go = true;
-  else if (kind == FXO_PARENT) go = fx_match_limit(buy, t.p0[k], b, px);
-  else go = (m & FXO_ACTIVE) && (fx_match_stop(buy, t.p0[k], b, px) || fx_match_limit(buy, t.p1[k], b, px));
+  if (kind == FXO_MARKET) { go = true; px = fx_market_price(s, buy, b); }
+  else if (kind == FXO_PARENT) go = fx_match_limit(s, buy, t.p0[k], b, px);
+  else go = (m & FXO_ACTIVE) && (fx_match_stop(s, buy, t.p0[k], b, px) || fx_match_limit(s, buy, t.p1[k], b, px));
   if (!go) return;
   // Completed or Margin: either way the entry leaves the table.  A child that completes cancels its sibling, a child
   // or parent that goes Margin cancels its whole group -- for a PAIR both mean "the pair is gone".

@@ -544,7 +544,7 @@ __device__ __forceinline__ void fx_step_env(const FxKernelParams& P, const void*
           }
           carry = 0u;
           double px_lane = 0.0;  // execution price of this lane's entry, should it trade on this bar
-          const bool hit = fx_entry_fill(m, p0, p1, b, px_lane);
+          const bool hit = fx_entry_fill(c.slippage_perc, m, p0, p1, b, px_lane);
           uint32_t hm = __ballot_sync(FX_FULL, valid && !(m & FXO_DEAD) && hit);
           while (hm) {
             const int l = __ffs(hm) - 1;

@@ -87,7 +87,7 @@ typedef struct FxConfig {
   /* default_broker -> backtrader BackBroker                          broker_plugins/default_broker.py:35-53 */
   double commission;                /* fraction of notional */
   double leverage;
-  double slippage_perc;             /* must be 0 (not yet supported) */
+  double slippage_perc;             /* fraction of price per fill, set_slippage_perc(perc, slip_open/limit/match=True) */
   int32_t children_same_bar;        /* 0 (backtrader: bracket children activate next cycle) | 1 */
 
   /* strategy plugin                                                  strategy_plugins/direct_{fixed,atr}_sltp.py */

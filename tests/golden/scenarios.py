@@ -99,6 +99,15 @@ SCENARIOS = [
          actions=("sticky", 4, 0.7), steps=260),
     dict(name="default_price_open", data=("synth", 300, 0, 71), cfg={"price_column": "OPEN", "window_size": 8},
          plugins=_pl(), actions=("sticky", 5, 0.8), steps=260),
+    # slippage (default_broker.py:39-51: set_slippage_perc(perc, slip_open=True, slip_limit=True, slip_match=True))
+    dict(name="slip_default_sample", data=("fixture", "eurusd_sample"),     # market orders; OPEN often outside [LOW, HIGH]
+         cfg={"slippage_perc": 2e-4, "commission": 1e-5}, plugins=_pl(), actions=("sticky", 21, 0.5), steps=480),
+    dict(name="slip_fixed_brackets", data=("synth", 600, 0, 72),           # limit parents, stop / limit children
+         cfg={"slippage": 1.5e-4, "sl_pips": 4.0, "tp_pips": 6.0}, plugins=_pl(strategy="direct_fixed_sltp"),
+         actions=("random", 22), steps=560),
+    dict(name="slip_atr_lev_sharpe", data=("synth", 600, 1, 73),
+         cfg={"slippage_perc": 5e-5, "leverage": 4.0, "commission": 2e-5, "atr_period": 6},
+         plugins=_pl(strategy="direct_atr_sltp", reward="sharpe_reward"), actions=("sticky", 23, 0.6), steps=560),
 ]
 
 

@@ -141,14 +141,15 @@ int hs_check_entry_fill(int n, unsigned seed) {
     const uint32_t kind = (uint32_t)(rnd() % 3);
     const uint32_t meta = kind | ((rnd() & 1) ? FXO_SELL : 0u) | ((rnd() & 1) ? FXO_ACTIVE : 0u);
     const double p0 = price(), p1 = price();
+    const double slip = (rnd() % 3 == 0) ? 0.0 : (double)(rnd() % 7) * 2.5e-4;  // with and without slippage
     double px = -1.0;
-    const bool hit = fx_entry_fill(meta, p0, p1, b, px);
+    const bool hit = fx_entry_fill(slip, meta, p0, p1, b, px);
     const bool buy = !(meta & FXO_SELL);
     double ref_px = b.o;
     bool ref;
-    if (kind == FXO_MARKET) ref = true;
-    else if (kind == FXO_PARENT) ref = fx_match_limit(buy, p0, b, ref_px);
-    else ref = fx_match_stop(buy, p0, b, ref_px) || fx_match_limit(buy, p1, b, ref_px);
+    if (kind == FXO_MARKET) { ref = true; ref_px = fx_market_price(slip, buy, b); }
+    else if (kind == FXO_PARENT) ref = fx_match_limit(slip, buy, p0, b, ref_px);
+    else ref = fx_match_stop(slip, buy, p0, b, ref_px) || fx_match_limit(slip, buy, p1, b, ref_px);
     if (hit != ref || hit != fx_entry_hits(meta, p0, p1, b) || (hit && px != ref_px)) bad++;
   }
   return bad;

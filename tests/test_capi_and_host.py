@@ -47,7 +47,7 @@ def test_create_validates_and_fails_loudly_without_gpu():
     h = C.c_void_p()
     assert L.fxenv_create(C.byref(cfg), C.byref(h)) == -1
     assert b"ABI mismatch" in L.fxenv_last_error(None)
-    cfg = _lower({**S.DEFAULTS, "slippage": 0.001})
+    cfg = _lower({**S.DEFAULTS, "slippage": 1.5})
     assert L.fxenv_create(C.byref(cfg), C.byref(h)) == -1 and b"slippage" in L.fxenv_last_error(None)
     if not torch.cuda.is_available():
         cfg = _lower({**S.DEFAULTS})

@@ -75,6 +75,8 @@ VEC_CASES = {
     "cfg1_default": (dict(window_size=32), {}, {}),
     "commission_leverage_relvol": (dict(window_size=16, commission=2e-5, leverage=5.0, rel_volume=0.3,
                                         max_order_volume=9000.0), dict(strategy="direct_atr_sltp"), {}),
+    "slippage_fixed_brackets": (dict(window_size=16, slippage_perc=2e-4, commission=1e-5, sl_pips=4.0, tp_pips=6.0),
+                                dict(strategy="direct_fixed_sltp"), {}),
     "margin_heavy_fixed": (dict(window_size=8, position_size=6000.0, commission=5e-5, sl_pips=4.0, tp_pips=6.0),
                            dict(strategy="direct_fixed_sltp", reward="dd_penalized_reward"), {}),
 }
