@@ -218,6 +218,7 @@ def run_ours(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=dev)
     cfg, candles, minutes, N, D, algo_bytes, desc = build_workload(args.workload, args.envs)
     K, Wm = args.steps, max(3, args.warmup)
+    cfg.auto_reset = 1   # auto-reset on (episodes span the table, so `terminated_frac` stays 0 in a run)
     env = VecFxEnv(cfg, candles, minutes, device=dev)
     # envs are sharded by rank: global env id = rank * N + i (no collective in the data path)
     check_pair_alignment(N, cfg.num_pairs)
@@ -309,7 +310,7 @@ def run_ours(args, rank, world, local_rank):
                        "l2": f"obs rows rotate through a {slots}-slot ring ({slots * N * D * 4 / 2**20:.0f} MiB > 126 MiB L2)",
                        "engine": (f"persistent launch: {chunk} steps per launch, warps pull (step, env) tickets, per-env dependencies"
                                   if engine == "persistent" else f"CUDA graph of {chunk} single-step launches (programmatic dependent launch)"),
-                       "order_overflow_envs": overflow,
+                       "auto_reset": True, "order_overflow_envs": overflow,
                        "terminated_frac": term_frac},
             "clocks": clocks,
             "e2e": {"value": e2e_rate, "unit": "env-steps/s", "h2d_bytes_per_step": N * 4,
