@@ -323,3 +323,36 @@ def test_gpu_nan_inf_feature_values_follow_nan_to_num():
         assert np.all(np.isfinite(g[0]))
         compare_step(f"nan/inf step {k}", g, o)
     gpu.close()
+
+
+@pytest.mark.parametrize("case", ["cfg5_atr_fw512_sharpe_4pairs", "cfg3_atr_fw256_dd", "slippage_fixed_brackets"])
+def test_step_many_engines_agree_on_other_kernels(case):
+    """Same check as above for the other template instantiations of the persistent kernel (ATR sizing, Sharpe ring staged
+    per env-step in shared memory that the warp reuses for its next env, drawdown state, several pairs, slippage), with
+    auto-reset and short episodes so that terminations and restarts happen inside the batches."""
+    import os
+    from gym_fx_b200.vec_env import VecFxEnv
+    cfgd, plugins, kw = VEC_CASES[case]
+    N, T, K = 384, 6000, 80
+    cfg, candles, minutes = _mk(cfgd, plugins, N, T=T, order_capacity=512, auto_reset=True, episode_bars=70, **kw)
+    starts = torch.as_tensor(start_offsets(N, T, 400, 300))
+    acts = torch.randint(0, 3, (2, K, N), dtype=torch.int32, generator=torch.Generator().manual_seed(3)).cuda()
+    outs = []
+    for dbg in ("16", "8"):
+        os.environ["FXENV_DEBUG"] = dbg
+        try:
+            env = VecFxEnv(cfg, candles, minutes)
+        finally:
+            del os.environ["FXENV_DEBUG"]
+        env.reset(starts)
+        ring = torch.zeros((2, N, env.obs_dim), dtype=torch.float32, device="cuda")
+        rews = torch.zeros((2, K, N), dtype=torch.float32, device="cuda")
+        terms = torch.zeros((2, K, N), dtype=torch.uint8, device="cuda")
+        for b in range(2):
+            env.step_many(acts[b], ring, rews[b], terms[b])
+        torch.cuda.synchronize()
+        outs.append((ring, rews, terms, env.get_state()))
+        env.close()
+    a, b = outs
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]) and bytes(a[3]) == bytes(b[3])
+    assert int(a[2].sum()) >= N and float(a[1].abs().sum()) > 0.0  # every env ended (and restarted) at least once
