@@ -143,6 +143,22 @@ class VecFxEnv:
         return {k: o[:, off:off + int(np.prod(shape))].reshape((o.shape[0],) + tuple(shape))
                 for k, (off, shape) in self.layout.items()}
 
+    def summary(self) -> Dict[str, Any]:
+        """Per-env end-of-run summary (GymFxEnv.summary, app/env.py:256-271 -> default_metrics.summarize :22-60) as device
+        tensors, plus fleet aggregates.  Only the fields the reference can fill on the live path exist (App. B #12):
+        equity-derived ones, the closed-trade counter and the commission paid."""
+        i = self.info()
+        ic = float(self.cfg.initial_cash)
+        eq = i["equity"]
+        ret = eq / ic - 1.0 if ic else torch.zeros_like(eq)
+        return {
+            "initial_cash": ic, "final_equity": eq, "total_return": ret, "trades_total": i["trades"],
+            "commission_paid": i["commission_paid"], "position": i["position"], "bar_index": i["bar_index"],
+            "mean_total_return": float(ret.mean()), "min_total_return": float(ret.min()),
+            "max_total_return": float(ret.max()), "mean_trades": float(i["trades"].double().mean()),
+            "order_overflow_envs": int((i["flags"] & 16).ne(0).sum()),
+        }
+
     def launch_count(self) -> int:
         return int(self.L.fxenv_launch_count(self._h))
 

@@ -251,6 +251,9 @@ def test_step_many_graph_and_step_host_match_step(cfg2_full):
         assert torch.equal(rew.cpu(), h_rew) and torch.equal(obs.cpu(), h_obs)
     assert torch.equal(obs, ring[(K - 1) % 2])
     assert torch.equal(a_env.info()["equity"], b_env.info()["equity"])
+    summ = a_env.summary()
+    assert torch.equal(summ["final_equity"], a_env.info()["equity"]) and summ["order_overflow_envs"] == 0
+    assert abs(summ["mean_total_return"] - float((a_env.info()["equity"] / 10000.0 - 1.0).mean())) < 1e-12
     # snapshot / restore round trip
     blob = a_env.get_state()
     ref = [a_env.step(acts[k])[1].clone() for k in range(3)]
