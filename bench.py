@@ -79,13 +79,34 @@ def build_workload(name, envs_override=None):
 
 
 class ClockSampler:
-    """nvidia-smi clock / throttle-reason sampler running during the timed region (B200_PROFILING.md)."""
+    """SM clock / throttle-reason sampler running DURING the timed region (B200_PROFILING.md).  NVML polled every ~2 ms
+    from a thread (the timed region is tens of milliseconds, too short for `nvidia-smi -lms`); falls back to nvidia-smi."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.rows, self.proc = [], None
+        self.rows, self.proc, self.nvml, self._stop = [], None, None, False
+        self.sm, self.mx, self.bits = [], None, 0
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            try:
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(index).uuid)   # robust to CUDA_VISIBLE_DEVICES
+                try:
+                    self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+                except Exception:
+                    self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nvml = pynvml
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.th = threading.Thread(target=self._poll, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "50", "-i", str(index)], stdout=subprocess.PIPE, text=True)
@@ -94,11 +115,32 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self._stop:
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
+                self.bits |= int(n.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception:
+                try:
+                    self.bits |= int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                except Exception:
+                    pass
+            time.sleep(0.002)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        if self.nvml is not None:
+            self._stop = True
+            self.th.join(timeout=1)
+            n = self.nvml
+            names = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+            reasons = sorted(nm for nm, bit in names if self.bits & bit)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.mx, "reasons": reasons,
+                    "samples": len(self.sm), "source": "nvml, 2 ms polling during the timed region"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.12)
@@ -112,7 +154,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "source": "nvidia-smi -lms 50"}
 
 
 def measured_peak_gbs():
