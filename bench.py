@@ -268,9 +268,7 @@ def run_ours(args, rank, world, local_rank):
     env.reset(starts)
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
-    chunk = min(K, 500)                      # graph length; K is covered by ceil(K/chunk) replays
-    while K % chunk:
-        chunk -= 1
+    chunk = min(K, 500)                      # steps per fxenv_step_many batch; K = full batches + one remainder batch
     acts = torch.randint(0, 3, (chunk, N), generator=gen, device=dev, dtype=torch.int32)
     slots = max(2, -(-int(L2_BYTES * 1.8) // (N * D * 4)))  # ring > 1.8x L2 so stores cannot just sit in L2
     ring = torch.empty((slots, N, D), dtype=torch.float32, device=dev)
@@ -282,6 +280,8 @@ def run_ours(args, rank, world, local_rank):
     wchunks = -(-Wm // chunk)
     for _ in range(max(1, wchunks)):
         env.step_many(acts, ring, rews, terms)
+    if K % chunk:                            # the remainder batch has its own launch sequence: instantiate it now too
+        env.step_many(acts[:K % chunk], ring, rews[:K % chunk], terms[:K % chunk])
     torch.cuda.synchronize(dev)
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -293,6 +293,9 @@ def run_ours(args, rank, world, local_rank):
     ev0.record(stream)
     for _ in range(K // chunk):
         env.step_many(acts, ring, rews, terms)
+    if K % chunk:
+        r = K % chunk
+        env.step_many(acts[:r], ring, rews[:r], terms[:r])
     ev1.record(stream)
     torch.cuda.synchronize(dev)
     if dist:
@@ -340,7 +343,7 @@ def run_ours(args, rank, world, local_rank):
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
                 per_step = json.load(fh).get(args.workload + "_per_step")
-                traffic = per_step * (K // max(1, int(launches))) if per_step and args.envs is None else None
+                traffic = per_step * K / max(1, int(launches)) if per_step and args.envs is None else None
         except Exception:
             pass
         line = {
@@ -362,7 +365,7 @@ def run_ours(args, rank, world, local_rank):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
                          "kernel": "fx_rollout_kernel" if engine == "persistent" else "fx_step_kernel",
-                         "algorithmic_bytes_per_launch": N * algo_bytes * (K // max(1, int(launches))),
+                         "algorithmic_bytes_per_launch": N * algo_bytes * K / max(1, int(launches)),
                          "avg_launch_us": ms_max * 1e3 / max(1, int(launches)),
                          "note": "achieved = algorithmic bytes of the timed region / its CUDA-event duration (the "
                                  "region is back-to-back launches of this one kernel); traffic = ncu dram bytes per env-step x envs"},

@@ -47,12 +47,17 @@ struct FxEnv {
   float* h_reward = nullptr;
   uint8_t* h_term = nullptr;
   // fxenv_step_many graph cache (one entry: the last pointer set)
-  cudaGraphExec_t gexec = nullptr;
-  const void* g_actions = nullptr;
-  float* g_obs = nullptr;
-  float* g_reward = nullptr;
-  uint8_t* g_term = nullptr;
-  int g_steps = 0, g_slots = 0;
+  // fxenv_step_many, graph engine: the two most recent launch sequences, keyed by the pointer set and sizes
+  struct CachedGraph {
+    cudaGraphExec_t exec = nullptr;
+    const void* actions = nullptr;
+    float* obs = nullptr;
+    float* reward = nullptr;
+    uint8_t* term = nullptr;
+    int steps = 0, slots = 0;
+    uint64_t used = 0;
+  } graphs[2];
+  uint64_t graph_clock = 0;
 };
 
 namespace {
@@ -121,7 +126,8 @@ int require_ready(FxEnv* env, bool need_reset) {
 }
 
 void drop_graph(FxEnv* env) {
-  if (env->gexec) { cudaGraphExecDestroy(env->gexec); env->gexec = nullptr; }
+  for (auto& g : env->graphs)
+    if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
 }
 
 }  // namespace
@@ -357,23 +363,27 @@ int fxenv_step_many(FxEnv* env, int n_steps, const void* actions_dev, float* obs
     env->launches += n_steps;
     return FXENV_OK;
   }
-  const bool hit = env->gexec && env->g_actions == actions_dev && env->g_obs == obs_dev && env->g_reward == reward_dev &&
-                   env->g_term == terminated_dev && env->g_steps == n_steps && env->g_slots == obs_slots;
-  if (!hit) {
-    drop_graph(env);
+  FxEnv::CachedGraph* slot = nullptr;
+  for (auto& g : env->graphs)
+    if (g.exec && g.actions == actions_dev && g.obs == obs_dev && g.reward == reward_dev && g.term == terminated_dev &&
+        g.steps == n_steps && g.slots == obs_slots) slot = &g;
+  if (!slot) {
+    slot = (env->graphs[0].used <= env->graphs[1].used) ? &env->graphs[0] : &env->graphs[1];  // least recently used
+    if (slot->exec) { cudaGraphExecDestroy(slot->exec); slot->exec = nullptr; }
     cudaGraph_t graph = nullptr;
     FX_CUDA(env, cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
     cudaError_t e = enqueue(stream);
     cudaError_t e2 = cudaStreamEndCapture(stream, &graph);
     if (e != cudaSuccess) { if (graph) cudaGraphDestroy(graph); return cuda_fail(env, e, "capture: fx_launch_step"); }
     if (e2 != cudaSuccess) return cuda_fail(env, e2, "cudaStreamEndCapture");
-    e = cudaGraphInstantiate(&env->gexec, graph, 0);
+    e = cudaGraphInstantiate(&slot->exec, graph, 0);
     cudaGraphDestroy(graph);
-    if (e != cudaSuccess) { env->gexec = nullptr; return cuda_fail(env, e, "cudaGraphInstantiate"); }
-    env->g_actions = actions_dev; env->g_obs = obs_dev; env->g_reward = reward_dev; env->g_term = terminated_dev;
-    env->g_steps = n_steps; env->g_slots = obs_slots;
+    if (e != cudaSuccess) { slot->exec = nullptr; return cuda_fail(env, e, "cudaGraphInstantiate"); }
+    slot->actions = actions_dev; slot->obs = obs_dev; slot->reward = reward_dev; slot->term = terminated_dev;
+    slot->steps = n_steps; slot->slots = obs_slots;
   }
-  FX_CUDA(env, cudaGraphLaunch(env->gexec, stream));
+  slot->used = ++env->graph_clock;
+  FX_CUDA(env, cudaGraphLaunch(slot->exec, stream));
   env->launches += n_steps;
   return FXENV_OK;
 }
