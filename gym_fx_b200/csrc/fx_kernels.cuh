@@ -49,7 +49,9 @@ struct FxKernelParams {
   long long* timing;        // debug (FXENV_TIMING=1): [N][FX_NSTAMP] clock64() phase stamps of the last step, else nullptr
   int32_t obs_dim;
   int32_t cap;              // logical order-table capacity (multiple of 32); arrays hold cap + FXO_SLACK
-  int32_t debug;            // timing experiments only (FXENV_DEBUG): 1 skip obs windows, 2 skip broker/strategy/reward
+  int32_t debug;            // timing experiments only (env FXENV_DEBUG, bit mask): 1 skip obs windows, 2 skip broker /
+                            // strategy / reward, 4 plain launches (no programmatic dependent launch), 8 step_many always as
+                            // the graph of single steps, 16 step_many always as the persistent launch
   int32_t resident_blocks;  // CTAs of the persistent rollout kernel resident at once on this device (SMs x occupancy)
   int32_t tame_data;        // 1: every loaded table value is finite and |x| < 1e100 (no NaN can arise in a z-score)
   int32_t fast_features;    // 5: F == n_cols == 5 with identity columns (the [W][5] block is one contiguous span)
