@@ -359,3 +359,33 @@ def test_step_many_engines_agree_on_other_kernels(case):
     a, b = outs
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]) and bytes(a[3]) == bytes(b[3])
     assert int(a[2].sum()) >= N and float(a[1].abs().sum()) > 0.0  # every env ended (and restarted) at least once
+
+
+@pytest.mark.parametrize("N,K", [(1, 60), (33, 40), (5000, 12)])
+def test_step_many_edge_sizes_match_single_steps(N, K):
+    """Persistent launch with one env, a ragged warp count, and more envs than resident warps; a one-slot observation
+    ring (every step overwrites the same rows): identical to K calls of fxenv_step."""
+    import os
+    from gym_fx_b200.vec_env import VecFxEnv
+    cfgd, plugins, kw = VEC_CASES["cfg2_fixed_fw128_pnl"]
+    T = 3000
+    cfg, candles, minutes = _mk(cfgd, plugins, N, T=T, order_capacity=256, **kw)
+    starts = torch.as_tensor(start_offsets(N, T, K + 10, 300))
+    acts = torch.randint(0, 3, (K, N), dtype=torch.int32, generator=torch.Generator().manual_seed(N)).cuda()
+    os.environ["FXENV_DEBUG"] = "16"
+    try:
+        many = VecFxEnv(cfg, candles, minutes)
+    finally:
+        del os.environ["FXENV_DEBUG"]
+    single = VecFxEnv(cfg, candles, minutes)
+    many.reset(starts); single.reset(starts)
+    assert many.step_many_engine(K) == "persistent"
+    ring = torch.zeros((1, N, many.obs_dim), dtype=torch.float32, device="cuda")
+    rews = torch.zeros((K, N), dtype=torch.float32, device="cuda")
+    terms = torch.zeros((K, N), dtype=torch.uint8, device="cuda")
+    many.step_many(acts, ring, rews, terms)
+    for k in range(K):
+        obs, rew, term, _, _ = single.step(acts[k])
+        assert torch.equal(rew, rews[k]) and torch.equal(term.to(torch.uint8), terms[k]), k
+    assert torch.equal(obs, ring[0]) and bytes(many.get_state()) == bytes(single.get_state())
+    many.close(); single.close()
