@@ -363,6 +363,7 @@ def run_ours(args, rank, world, local_rank):
                     "note": "fxenv_step_host: pinned host buffers, synchronous per step (PCIe-bound)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "frac_of_nominal_8TBs": achieved / 8000.0,
                          "traffic": traffic, "peak_source": peak_src,
                          "kernel": "fx_rollout_kernel" if engine == "persistent" else "fx_step_kernel",
                          "algorithmic_bytes_per_launch": N * algo_bytes * K / max(1, int(launches)),
