@@ -1,23 +1,25 @@
 // fx_kernels.cu -- sm_100a kernels of the fused gym-fx env.step().
 //
-// fx_step_kernel<STRAT, REWARD, FAST5>: ONE launch = one env.step() for all N envs; one warp owns one env from start
-// to finish and a CTA is just FX_WARPS independent warps (no block barrier), so the ~28 warps an SM owns at 4096 envs
-// are all resident and progress concurrently.  Per warp:
+// fx_step_env<STRAT, REWARD, FAST5> is the whole env-step of ONE env by ONE warp (no block barrier anywhere):
 //
-//   prefetch right after the state loads, lane 0 issues ONE TMA bulk copy (cp.async.bulk + mbarrier) of the env's
-//            candle window (W rows x n_cols fp64, one contiguous span of the table) into the warp's shared memory;
-//            it lands while the broker runs;
+//   load     one round trip: the env's state scalars, its action, the candle of this step (saved by the previous step)
+//            and the first 32 orders of its table;
+//   prefetch lane 0 issues TMA bulk copies (cp.async.bulk + mbarrier) of the env's candle window (W rows x n_cols fp64,
+//            one contiguous span of the table) and of the bar's z-score statistics into the warp's shared memory;
+//            they land while the broker runs;
 //   broker   backtrader's per-bar pass as ONE streaming sweep over the env's order table, 32 orders (one per lane) at
-//            a time in registers: bracket activation + trigger test (ballot), the few orders that trade are executed
-//            in FIFO order by uniform scalar fp64 code (fx_core.cuh) with their fields broadcast by shuffle, then
-//            stable compaction + write-back of what changed.  check_submitted is decided lane-parallel by a rigorous
-//            cash bound (the exact sequential simulation is a cold path).  Then apply_action, publish, reward;
+//            a time in registers with the next chunk in flight: bracket activation + trigger test and execution price
+//            per lane (ballot), the few orders that trade are executed in FIFO order by uniform scalar fp64 code
+//            (fx_core.cuh) with their fields broadcast by shuffle, then stable compaction + write-back of what
+//            changed.  check_submitted is decided by a rigorous cash bound (the exact sequential simulation is a cold
+//            path).  Then apply_action, publish, reward, write-back;
 //   observe  the observation row ([W,F] z-scored features | prices | returns | 4 agent scalars) is produced from the
 //            staged window: fp64 math, coalesced fp32 streaming stores (>99% of the bytes).
 //
-// The kernel is compiled once per (strategy, reward, 5-feature fast path) so each instance only carries the code its
-// configuration can reach.
-// No tensor cores: there is no contraction on this path.
+// Two kernels wrap it: fx_step_kernel (one launch = one step of all N envs, one env per one-warp CTA, programmatic
+// dependent launch) and fx_rollout_kernel (one launch = K steps: persistent warps pull (step, env) tickets and only
+// honour per-env dependencies).  Both are compiled once per (strategy, reward, 5-feature fast path) so each instance
+// only carries the code its configuration can reach.  No tensor cores: there is no contraction on this path.
 //
 // Reference call stack being replaced: app/env.py:131-172 -> app/bt_bridge.py:119-150 -> strategy / reward /
 // preprocessor plugins + backtrader (per-function citations in fx_core.cuh).
