@@ -138,6 +138,21 @@ def test_default_strategy_driver_modes():
     import random
     r = random.Random(5)
     assert a[:1] == [r.choice([0, 1, 2])]
+    # the whole stream, per step and as an up-front [steps, envs] table for VecFxEnv.step_many
+    r = random.Random(9)
+    want = [r.choice([0, 1, 2]) for _ in range(12)]
+    p = Plugin({"driver_mode": "random", "seed": 9})
+    assert [p.decide_action(None, None, k) for k in range(12)] == want
+    tab = Plugin({"driver_mode": "random", "seed": 9}).action_table(12, 3)
+    assert tab.shape == (12, 3) and tab.dtype.name == "int32" and tab[:, 0].tolist() == want and (tab[:, 2] == tab[:, 0]).all()
+    import os, tempfile
+    with tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False) as fh:
+        fh.write("DATE_TIME,action\na,2\nb,0\nc,1\n")
+    try:
+        rp = Plugin({"driver_mode": "replay", "replay_actions_file": fh.name})
+        assert [rp.decide_action(None, None, k) for k in range(5)] == [2, 0, 1, 0, 0]
+    finally:
+        os.unlink(fh.name)
 
 
 def test_metrics_summary_matches_reference_golden_fields():
