@@ -176,7 +176,8 @@ __device__ __forceinline__ float fx_finish_t(float v, float clipf) {
   return isinf(v) ? (v > 0.0f ? clipf : -clipf) : v;
 }
 
-template <bool FAST5, bool CLIP, bool TAME>
+// LONG: windows of several hundred rows, where loop overhead outweighs instruction-cache footprint (the loops are unrolled)
+template <bool FAST5, bool CLIP, bool TAME, bool LONG>
 __device__ __noinline__ void fx_emit_windows_t(const FxKernelParams& P, int lane, int s, bool scale,
                                                const double* __restrict__ win, const double* sstat,
                                                float* __restrict__ out) {
@@ -200,14 +201,23 @@ __device__ __noinline__ void fx_emit_windows_t(const FxKernelParams& P, int lane
         const double m0 = z0 ? sstat[2 * f0] : 0.0, r0 = z0 ? sstat[2 * f0 + 1] : 1.0;
         const double m1 = z1 ? sstat[2 * f1] : 0.0, r1 = z1 ? sstat[2 * f1 + 1] : 1.0;
         const int npair = total >> 1;  // total = 5 W; an odd W leaves one tail element
-#pragma unroll 4
-        for (int q = lane; q < npair; q += 30) {
-          const double x0 = win[2 * q], x1 = win[2 * q + 1];
-          float2 v;
-          v.x = fx_finish_t<CLIP, TAME>((float)((x0 - m0) * r0), clipf);
-          v.y = fx_finish_t<CLIP, TAME>((float)((x1 - m1) * r1), clipf);
+        // Short windows: not unrolled on purpose -- 16 warps per SM sit at different places of a ~65 KB kernel, and the
+        // smaller loop body is worth more in instruction-cache hits than the saved loop overhead (measured, cfg2 W=128:
+        // unroll 4 -> 1 = 13.6 -> 12.5 us; cfg5 W=512: 72.8 -> 79.9 us, hence the LONG variant).
+#define FX_PAIR_BODY                                                        \
+          const double x0 = win[2 * q], x1 = win[2 * q + 1];                \
+          float2 v;                                                         \
+          v.x = fx_finish_t<CLIP, TAME>((float)((x0 - m0) * r0), clipf);    \
+          v.y = fx_finish_t<CLIP, TAME>((float)((x1 - m1) * r1), clipf);    \
           __stcs(reinterpret_cast<float2*>(out) + q, v);
+        if (LONG) {
+#pragma unroll 4
+          for (int q = lane; q < npair; q += 30) { FX_PAIR_BODY }
+        } else {
+#pragma unroll 1
+          for (int q = lane; q < npair; q += 30) { FX_PAIR_BODY }
         }
+#undef FX_PAIR_BODY
         if ((total & 1) && lane == 0) {
           const int j = total - 1, f = j % 5;
           const bool z = scale && !c.feature_binary[f];
@@ -235,17 +245,23 @@ __device__ __noinline__ void fx_emit_windows_t(const FxKernelParams& P, int lane
   if (inc_price) {
     const int pc = c.price_col;
     float* __restrict__ op = out + off;
-#pragma unroll 4
-    for (int w = lane; w < W; w += 32) {
-      int k = w - pad;
-      if (k < 0) k = 0;
-      int k1 = w - 1 - pad;
-      if (k1 < 0) k1 = 0;
-      const double p = win[k * C + pc];
-      const double prev = win[k1 * C + pc];
-      __stcs(op + w, (float)p);
+#define FX_PRICE_BODY                                                       \
+      int k = w - pad;                                                      \
+      if (k < 0) k = 0;                                                     \
+      int k1 = w - 1 - pad;                                                 \
+      if (k1 < 0) k1 = 0;                                                   \
+      const double p = win[k * C + pc];                                     \
+      const double prev = win[k1 * C + pc];                                 \
+      __stcs(op + w, (float)p);                                             \
       __stcs(op + W + w, (w == 0) ? 0.0f : (float)(p - prev));
+    if (LONG) {
+#pragma unroll 4
+      for (int w = lane; w < W; w += 32) { FX_PRICE_BODY }
+    } else {
+#pragma unroll 1
+      for (int w = lane; w < W; w += 32) { FX_PRICE_BODY }
     }
+#undef FX_PRICE_BODY
   }
 }
 
@@ -253,11 +269,16 @@ template <bool FAST5>
 __device__ __forceinline__ void fx_emit_windows(const FxKernelParams& P, int lane, int s, bool scale,
                                                 const double* __restrict__ win, const double* sstat,
                                                 float* __restrict__ out) {
+  const bool lng = P.cfg.window_size >= 384;
   if (P.cfg.feature_clip > 0.0) {
-    if (P.tame_data) fx_emit_windows_t<FAST5, true, true>(P, lane, s, scale, win, sstat, out);
-    else fx_emit_windows_t<FAST5, true, false>(P, lane, s, scale, win, sstat, out);
+    if (P.tame_data) {
+      if (lng) fx_emit_windows_t<FAST5, true, true, true>(P, lane, s, scale, win, sstat, out);
+      else fx_emit_windows_t<FAST5, true, true, false>(P, lane, s, scale, win, sstat, out);
+    } else {
+      fx_emit_windows_t<FAST5, true, false, false>(P, lane, s, scale, win, sstat, out);
+    }
   } else {
-    fx_emit_windows_t<FAST5, false, false>(P, lane, s, scale, win, sstat, out);
+    fx_emit_windows_t<FAST5, false, false, false>(P, lane, s, scale, win, sstat, out);
   }
 }
 
