@@ -174,6 +174,8 @@ int fxenv_create(const FxConfig* cfg, FxEnv** out) {
     for (int i = 0; i < 5; i++) if (c.feature_cols[i] != i) env->P.fast_features = 0;
   }
   ce = fx_configure_kernels(env->P);
+  if (const char* rb = getenv("FXENV_ROLLOUT_BLOCKS"))  // timing experiments only: grid of the persistent launch
+    if (atoi(rb) > 0 && atoi(rb) < env->P.resident_blocks) env->P.resident_blocks = atoi(rb);
   if (ce != cudaSuccess) { delete env; return cuda_fail(nullptr, ce, "window_size * n_cols too large for shared memory"); }
   // one slab for the whole per-env state (snapshot == one memcpy)
   const size_t N = (size_t)c.num_envs;

@@ -785,8 +785,11 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
 // (many fills) only delay their own env.  No deadlock: the ticket an env-step waits for is lower than its own, and every
 // ticket handed out belongs to a running warp that needs nothing from higher tickets.  seq[] and the counter are zeroed
 // by a stream-ordered memset before the launch.
+#ifndef FX_ROLLOUT_MIN_BLOCKS
+#define FX_ROLLOUT_MIN_BLOCKS FX_MIN_BLOCKS
+#endif
 template <int STRAT, int REWARD, bool FAST5>
-__global__ void __launch_bounds__(FX_WARPS * 32, FX_MIN_BLOCKS)
+__global__ void __launch_bounds__(FX_WARPS * 32, FX_ROLLOUT_MIN_BLOCKS)
 fx_rollout_kernel(const __grid_constant__ FxKernelParams P, const char* __restrict__ actions, float* __restrict__ obs,
                   const int obs_slots, float* __restrict__ reward, uint8_t* __restrict__ terminated, const int n_steps) {
   extern __shared__ __align__(16) unsigned char fx_smem[];
