@@ -149,27 +149,38 @@ typedef struct FxInfoPtrs {
 
 int fxenv_abi_version(void);
 
+/* Replaces GymFxEnv.__init__ (app/env.py:36-97: config resolution, spaces, min_equity) and, per reset, build_cerebro /
+ * build_bt_broker (app/bt_bridge.py:207-238, broker_plugins/default_broker.py:35-53).  Validates the POD config and
+ * allocates the per-env device state; fails (no CPU path) when no CUDA device is available. */
 int fxenv_create(const FxConfig* cfg, FxEnv** out);
+/* Replaces GymFxEnv.close (app/env.py:177-178). */
 int fxenv_destroy(FxEnv* env);
 const char* fxenv_last_error(const FxEnv* env); /* env may be NULL: error of the last failed fxenv_create */
 
-/* Copies a host float64 [T, n_cols] row-major candle table (and optional int64 [T] minutes-since-epoch
+/* Replaces data_feed.load_data + build_bt_feed (data_feed_plugins/default_data_feed.py:36-79: the dataframe the env
+ * keeps, app/env.py:62-67, incl. its "too short for the window" ValueError).
+ * Copies a host float64 [T, n_cols] row-major candle table (and optional int64 [T] minutes-since-epoch
  * timestamps, needed only by the ATR session filter) to the device, and precomputes the per-bar rolling
  * z-score statistics.  Synchronous. */
 int fxenv_load_candles(FxEnv* env, int pair_id, const double* candles_host, int64_t T, const int64_t* minutes_host);
 
-/* Number of float32 per observation row and the offsets of its parts (flat layout):
+/* Replaces the observation_space bookkeeping of app/env.py:81-90.
+ * Number of float32 per observation row and the offsets of its parts (flat layout):
  * [features W*F | prices W | returns W | position | equity_norm | unrealized_pnl_norm | steps_remaining_norm] */
 int64_t fxenv_obs_dim(const FxEnv* env);
 
-/* start_bar_dev: int64 [num_envs] first bar (row of the pair's table) of each env's episode window, or NULL to
+/* Replaces GymFxEnv.reset (app/env.py:102-129: new bridge / broker / feed, first publish at bar 0).
+ * start_bar_dev: int64 [num_envs] first bar (row of the pair's table) of each env's episode window, or NULL to
  * keep the current ones (all 0 after create).  mask_dev: uint8 [num_envs], reset only where != 0, or NULL = all. */
 int fxenv_reset(FxEnv* env, const int64_t* start_bar_dev, const uint8_t* mask_dev, void* stream);
 
-/* Writes the observation of the current state (what reset() returns). obs_dev: float32 [num_envs, obs_dim]. */
+/* Replaces _make_observation for the current state (app/env.py:226-242 -> preprocessor.make_observation).
+ * Writes the observation of the current state (what reset() returns). obs_dev: float32 [num_envs, obs_dim]. */
 int fxenv_observe(FxEnv* env, float* obs_dev, void* stream);
 
-/* One env.step() for every env.  actions_dev: int32 [num_envs] (discrete) or float32 [num_envs] (continuous).
+/* Replaces GymFxEnv.step (app/env.py:131-172) and everything below it: BTBridgeStrategy.next (app/bt_bridge.py:119-150),
+ * the strategy / reward / preprocessor plugins and backtrader's broker pass.
+ * One env.step() for every env.  actions_dev: int32 [num_envs] (discrete) or float32 [num_envs] (continuous).
  * obs_dev float32 [num_envs, obs_dim]; reward_dev float32 [num_envs]; terminated_dev uint8 [num_envs].
  * reward64_dev: optional float64 [num_envs] copy of the reward before the float32 cast (may be NULL). */
 int fxenv_step(FxEnv* env, const void* actions_dev, float* obs_dev, float* reward_dev, uint8_t* terminated_dev,
@@ -187,13 +198,16 @@ int fxenv_step_many(FxEnv* env, int n_steps, const void* actions_dev, float* obs
 /* Which engine fxenv_step_many would use for a batch of n_steps (1 persistent launch / 0 graph of steps), <0 on error. */
 int fxenv_step_many_engine(const FxEnv* env, int n_steps);
 
-/* Reference-facing call with HOST buffers: H2D actions, one step, D2H obs/reward/terminated, then waits. */
+/* Same as fxenv_step for callers that hold numpy / host buffers like the reference's own loop (app/main.py:57-65,
+ * tools/smoke_test.py:79-83).  Reference-facing call with HOST buffers: H2D actions, one step, D2H obs/reward/terminated, then waits. */
 int fxenv_step_host(FxEnv* env, const void* actions_host, float* obs_host, float* reward_host,
                     uint8_t* terminated_host);
 
+/* Replaces GymFxEnv._make_info (app/env.py:244-254): zero-copy device views instead of a dict of Python floats. */
 int fxenv_get_info(FxEnv* env, FxInfoPtrs* out);
 
-/* Snapshot / restore of the whole env state (host buffer of fxenv_state_bytes() bytes). Synchronous. */
+/* No reference counterpart (its env cannot be cloned: one daemon thread per instance, app/bt_bridge.py:30-66).
+ * Snapshot / restore of the whole env state (host buffer of fxenv_state_bytes() bytes). Synchronous. */
 int64_t fxenv_state_bytes(const FxEnv* env);
 int fxenv_get_state(FxEnv* env, void* buf_host, int64_t nbytes);
 int fxenv_set_state(FxEnv* env, const void* buf_host, int64_t nbytes);
