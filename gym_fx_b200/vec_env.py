@@ -1,8 +1,8 @@
 """
 VecFxEnv -- N lock-stepped gym-fx environments on one GPU, torch tensors in and out, no host round trip.
 
-Semantics per env are those of the reference's GymFxEnv.reset/step (app/env.py:102-172); every step of all N
-envs is ONE launch of the fused sm_100a kernel in libfxenv.so.  torch is used only for device memory and streams.
+Semantics per env are those of the reference's GymFxEnv.reset/step (app/env.py:102-172); a step of all N envs is ONE
+launch of the fused sm_100a kernel in libfxenv.so, a batch of K steps with known actions ONE persistent launch.  torch is used only for device memory and streams.
 """
 from __future__ import annotations
 
@@ -109,8 +109,10 @@ class VecFxEnv:
         return obs, self.reward, self.terminated.view(torch.bool), self.truncated, self.info()
 
     def step_many(self, actions: torch.Tensor, obs_ring: torch.Tensor, rewards: torch.Tensor, terminated: torch.Tensor):
-        """K consecutive steps as one cached CUDA graph.  actions [K, N]; obs_ring [slots, N, D];
-        rewards float32 [K, N]; terminated uint8 [K, N]."""
+        """K consecutive steps with all actions supplied up front (replay / random / scripted drivers); identical results
+        to K calls of step().  actions [K, N]; obs_ring [slots, N, D] (step k writes slot k % slots); rewards float32
+        [K, N]; terminated uint8 [K, N].  The library runs the batch as one persistent launch or as a cached CUDA graph
+        of single steps (`step_many_engine`)."""
         K = actions.shape[0]
         rc = self.L.fxenv_step_many(self._h, int(K), actions.data_ptr(), obs_ring.data_ptr(), int(obs_ring.shape[0]),
                                     rewards.data_ptr(), terminated.data_ptr(), self._stream())
