@@ -87,24 +87,30 @@ def main():
     # rollout buffers; obs[t] is what the policy sees at step t, obs[H] bootstraps the value of the last state
     obs = torch.zeros((H + 1, N, D), device=dev)
     act = torch.zeros((H, N), dtype=torch.int32, device=dev)
+    act64 = torch.zeros((H, N), dtype=torch.int64, device=dev)
     logp = torch.zeros((H, N), device=dev)
     val = torch.zeros((H + 1, N), device=dev)
     rew = torch.zeros((H, N), device=dev)
     done = torch.zeros((H, N), device=dev)
     obs[0].copy_(env.obs)
 
+    gumbel = torch.zeros((H, N, 3), device=dev)
+    rew_v, done_v = rew.view(H, N), done.view(H, N)
+
     def rollout():
         with torch.no_grad():
+            # Gumbel noise for the whole rollout in three kernels instead of four per step
+            gumbel.uniform_(1e-9, 1.0 - 1e-9)
+            gumbel.log_().neg_().log_().neg_()
             for t in range(H):
                 logits, v = net(obs[t])
-                u = torch.rand_like(logits).clamp_(1e-9, 1.0 - 1e-9)
-                a = torch.argmax(logits - torch.log(-torch.log(u)), dim=-1)           # Gumbel-max sample
-                act[t].copy_(a)
-                logp[t].copy_(torch.log_softmax(logits, -1).gather(1, a[:, None]).squeeze(1))
+                torch.argmax(logits + gumbel[t], dim=-1, out=act64[t])                # Gumbel-max sample
+                act[t].copy_(act64[t])
+                logp[t].copy_(torch.log_softmax(logits, -1).gather(1, act64[t][:, None]).squeeze(1))
                 val[t].copy_(v)
                 _, r, term, _, _ = env.step(act[t], out_obs=obs[t + 1])               # fxenv_step on this stream
-                rew[t].copy_(r)
-                done[t].copy_(term)
+                rew_v[t].copy_(r)
+                done_v[t].copy_(term)
             val[H].copy_(net(obs[H])[1])
 
     graph = None
@@ -146,7 +152,7 @@ def main():
             ret = adv + val[:H]
             m, s = global_mean_std(adv, dist)
             adv = (adv - m) / s
-        b_obs, b_act = obs[:H].reshape(H * N, D), act.reshape(-1).long()
+        b_obs, b_act = obs[:H].reshape(H * N, D), act64.reshape(-1)
         b_logp, b_adv, b_ret = logp.reshape(-1), adv.reshape(-1), ret.reshape(-1)
         mb = (H * N) // args.minibatches
         for _ in range(args.epochs):
