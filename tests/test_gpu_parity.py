@@ -389,3 +389,63 @@ def test_step_many_edge_sizes_match_single_steps(N, K):
         assert torch.equal(rew, rews[k]) and torch.equal(term.to(torch.uint8), terms[k]), k
     assert torch.equal(obs, ring[0]) and bytes(many.get_state()) == bytes(single.get_state())
     many.close(); single.close()
+
+
+@pytest.mark.parametrize("case,N,pairs_kw", [
+    ("cfg3_atr_fw256_dd", 16384, {}),                       # BASELINE configs[2] at full size
+    ("cfg5_atr_fw512_sharpe_4pairs", 8192, None),           # BASELINE configs[4] (per GPU) at full size
+])
+def test_full_size_other_baseline_shapes(case, N, pairs_kw):
+    """At BASELINE's full sizes for the two large shapes: a batch through fxenv_step_many (the graph engine at these
+    sizes) is reproducible, independent of how many envs share the launch (every 16th env run alone gives the same
+    trajectory), keeps equity under the flat policy, and a sample of 48 envs matches the CPU oracle step by step."""
+    from gym_fx_b200.vec_env import VecFxEnv
+    cfgd, plugins, kw = VEC_CASES[case]
+    T, K = 1 << 15, 48
+    starts = start_offsets(N, T, K + 8, 300)
+    acts = np.random.default_rng(77).integers(0, 3, (K, N)).astype(np.int32)
+
+    def run(sel, actions):
+        cfg, candles, minutes = _mk(cfgd, plugins, len(sel), T=T, order_capacity=256, **kw)
+        env = VecFxEnv(cfg, candles, minutes)
+        env.reset(torch.as_tensor(starts[sel]))
+        ring = torch.zeros((1, len(sel), env.obs_dim), dtype=torch.float32, device="cuda")
+        rews = torch.zeros((K, len(sel)), dtype=torch.float32, device="cuda")
+        terms = torch.zeros((K, len(sel)), dtype=torch.uint8, device="cuda")
+        env.step_many(torch.as_tensor(np.ascontiguousarray(actions[:, sel])).cuda(), ring, rews, terms)
+        torch.cuda.synchronize()
+        out = (ring[0].cpu().numpy(), rews.cpu().numpy(), terms.cpu().numpy(),
+               {k: env.info()[k].cpu().numpy() for k in ("equity", "cash", "trades", "position", "bar_index", "flags")},
+               env.step_many_engine(K))
+        env.close()
+        return out, (cfg, candles, minutes)
+
+    allenv = np.arange(N)
+    (obs, rews, terms, inf, engine), _ = run(allenv, acts)
+    assert engine == "graph" and not np.any(inf["flags"] & 16)
+    (obs2, rews2, terms2, inf2, _), _ = run(allenv, acts)
+    assert np.array_equal(obs, obs2) and np.array_equal(rews, rews2) and np.array_equal(inf["equity"], inf2["equity"])
+    # same pair assignment needs the same (global id % pairs): take every 16th env (16 % 4 == 0)
+    sel = allenv[::16]
+    (obs_s, rews_s, terms_s, inf_s, _), (cfg_s, candles, minutes) = run(sel, acts)
+    if cfg_s.num_pairs > 1:
+        assert np.all(sel % cfg_s.num_pairs == 0)   # all of them trade pair 0 in both runs only if ids line up
+    if cfg_s.num_pairs == 1:
+        assert np.array_equal(obs[sel], obs_s) and np.array_equal(rews[:, sel], rews_s)
+        for key in ("equity", "cash", "trades", "position"):
+            assert np.array_equal(inf[key][sel], inf_s[key]), key
+    # sampled oracle at full size (local ids 0..47 keep their pair: id % pairs)
+    samp = np.arange(48)
+    cfg_o, _, _ = _mk(cfgd, plugins, len(samp), T=T, order_capacity=256, **kw)
+    orc = OracleVec(cfg_o, candles, minutes)
+    orc.reset(starts[samp])
+    for k in range(K):
+        oo = orc.step(acts[k, samp])
+        np.testing.assert_allclose(rews[k, samp], oo[1], rtol=1e-5, atol=1e-12, err_msg=f"{case} step {k}: reward")
+        assert np.array_equal(terms[k, samp], oo[3])
+    np.testing.assert_allclose(obs[samp], oo[0], rtol=1e-5, atol=2e-6, err_msg=f"{case}: last obs")
+    oi = orc.info()
+    assert np.array_equal(inf["equity"][samp], oi["equity"]) and np.array_equal(inf["trades"][samp], oi["trades"])
+    # flat policy: equity untouched (tools/smoke_test.py:113-118 of the reference)
+    (_, rews_f, _, inf_f, _), _ = run(allenv, np.zeros_like(acts))
+    assert np.all(inf_f["equity"] == 10000.0) and np.all(inf_f["trades"] == 0) and np.all(rews_f[1:] == 0.0)
