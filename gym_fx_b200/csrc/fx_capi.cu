@@ -315,7 +315,11 @@ int fxenv_step(FxEnv* env, const void* actions_dev, float* obs_dev, float* rewar
 }
 
 static bool batch_uses_rollout(const FxEnv* env, int n_steps) {
-  bool rollout = n_steps > 1 && (long long)env->P.cfg.num_envs <= 3ll * env->P.resident_blocks * FX_WARPS;
+  // measured (B200, us/step persistent vs graph): W=128 rows (3.6 KB) at 2048 / 4096 / 8192 / 16384 envs: 10.2 vs 15.7,
+  // 12.5 vs 20.6, 24.8 vs 30.6, 52.0 vs 53.0; cfg3 (16384 envs, 7.2 KB rows) 77.6 vs 68.2; cfg5 (8192 envs, 14 KB rows)
+  // 75.7 vs 74.6 -- the persistent launch pays a store-drain fence per env-step that grows with the row size
+  const bool few_waves = (long long)env->P.cfg.num_envs <= 3ll * env->P.resident_blocks * FX_WARPS;
+  bool rollout = n_steps > 1 && (few_waves || env->P.obs_dim <= 1024);
   if (env->P.debug & (4 | 8)) rollout = false;             // FXENV_DEBUG: force the graph of single steps (A/B timing)
   if ((env->P.debug & 16) && n_steps > 1) rollout = true;  // FXENV_DEBUG & 16: force the persistent launch
   return rollout;
@@ -345,10 +349,8 @@ int fxenv_step_many(FxEnv* env, int n_steps, const void* actions_dev, float* obs
     return cudaSuccess;
   };
   // Two ways to run a batch: (a) ONE persistent launch whose warps pull (step, env) tickets and honour per-env
-  // dependencies (fx_rollout_kernel) -- wins while the envs fill the device only a few times over, because the tail of a
-  // step (envs with many fills) overlaps the next step; (b) a CUDA graph of K single-step launches -- wins once the
-  // device is saturated anyway (measured on B200: cfg2/cfg4 4096 envs (a) 13.3 / 17.4 vs (b) 20.0 / 24.5 us per step;
-  // cfg3 16384 envs (a) 81.9 vs (b) 70.2; cfg5 8192 envs W=512 (a) 75.4 vs (b) 74.1).
+  // dependencies (fx_rollout_kernel) -- the tail of a step (envs with many fills) overlaps the next step; (b) a CUDA graph
+  // of K single-step launches -- wins for large observation rows once the device is saturated (see batch_uses_rollout).
   const bool rollout = batch_uses_rollout(env, n_steps);
   if (rollout) {
     if ((unsigned long long)N * (unsigned long long)n_steps >= (1ull << 31))
