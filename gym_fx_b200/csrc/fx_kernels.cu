@@ -387,14 +387,18 @@ template <int STRAT, int REWARD, bool FAST5>
 __device__ __forceinline__ void fx_step_env(const FxKernelParams& P, const void* __restrict__ actions, float* __restrict__ obs,
                                             float* __restrict__ reward, double* __restrict__ reward64,
                                             uint8_t* __restrict__ terminated, const int env, const int lane, const WarpSmem& ws,
-                                            const unsigned phase = 0u) {
+                                            const unsigned phase = 0u, const unsigned step_row = 0u, const unsigned obs_slot_row = 0u) {
+  // `actions` / `reward` / `terminated` / `obs` are the BASES of the caller's arrays (kernel parameters: they cost no
+  // registers); this env-step's element is at index step_row + env (step_row = step * num_envs) and its observation row
+  // at obs_slot_row + env (obs_slot_row = slot * num_envs).  Addresses are formed where they are used.
+#define FX_OBS_ROW() (obs + ((size_t)obs_slot_row + (size_t)env) * (size_t)P.obs_dim)
+#define FX_OUT_IDX() ((size_t)step_row + (size_t)env)
   const FxConfig& c = P.cfg;
   const FxDeviceState& st = P.st;
   const int C = c.n_cols;
   const int capP = P.cap + FXO_SLACK;
   const int pair = (c.num_pairs == 1) ? 0 : env % c.num_pairs;
   const FxPairTable& tb = P.pair[pair];
-  float* __restrict__ obs_row = obs + (int64_t)env * P.obs_dim;
 #ifdef FXENV_ENABLE_TIMING  // phase instrumentation build (make TIMING=1): tools/phase_timing.py
   long long* tstamp = P.timing ? P.timing + (int64_t)env * FX_NSTAMP : nullptr;
 #define FX_STAMP(i) do { if (tstamp && lane == 0) tstamp[i] = clock64(); } while (0)
@@ -424,8 +428,8 @@ __device__ __forceinline__ void fx_step_env(const FxKernelParams& P, const void*
   e.value = e.equity;
   int action_raw_i = 0;
   float action_raw_f = 0.0f;
-  if (c.action_mode == FX_ACTION_CONTINUOUS) action_raw_f = reinterpret_cast<const float*>(actions)[env];
-  else action_raw_i = reinterpret_cast<const int32_t*>(actions)[env];
+  if (c.action_mode == FX_ACTION_CONTINUOUS) action_raw_f = reinterpret_cast<const float*>(actions)[FX_OUT_IDX()];
+  else action_raw_i = reinterpret_cast<const int32_t*>(actions)[FX_OUT_IDX()];
   // the candle this call works on was saved by the previous call (FxDeviceState::nbar), and the first 32 orders of
   // the table sit at an address that only depends on the env: both travel in this same round trip
   const double2* __restrict__ nb2 = reinterpret_cast<const double2*>(st.nbar + (int64_t)env * 6);
@@ -471,10 +475,10 @@ __device__ __forceinline__ void fx_step_env(const FxKernelParams& P, const void*
       e.price = tb.candles[(start + t) * (int64_t)C + 3];
     }
     if (lane == 0) {
-      reward[env] = 0.0f;
-      if (reward64) reward64[env] = 0.0;
-      terminated[env] = c.auto_reset ? 0 : 1;
-      fx_write_scalars(P, e, total_bars, tb.candles[(start + e.bar_index - 1) * (int64_t)C + c.price_col], obs_row);
+      reward[FX_OUT_IDX()] = 0.0f;
+      if (reward64) reward64[FX_OUT_IDX()] = 0.0;
+      terminated[FX_OUT_IDX()] = c.auto_reset ? 0 : 1;
+      fx_write_scalars(P, e, total_bars, tb.candles[(start + e.bar_index - 1) * (int64_t)C + c.price_col], FX_OBS_ROW());
     }
     {
       const int s = e.bar_index;
@@ -484,7 +488,7 @@ __device__ __forceinline__ void fx_step_env(const FxKernelParams& P, const void*
       const int shift = fx_window_issue(tb, C, start, left, s - left, lane, ws);
       const bool scale = fx_prepare_stats(P, tb, env, lane, s, start, ws.stat);
       fx_window_wait(ws, phase);
-      fx_emit_windows<FAST5>(P, lane, s, scale, ws.win + shift, ws.stat, obs_row);
+      fx_emit_windows<FAST5>(P, lane, s, scale, ws.win + shift, ws.stat, FX_OBS_ROW());
     }
     return;
   }
@@ -706,13 +710,13 @@ __device__ __forceinline__ void fx_step_env(const FxKernelParams& P, const void*
       if (n_final != n) st.n_orders[env] = n_final;
       if (n_acc_new != n_acc) st.n_acc[env] = n_acc_new;
       if (sub_need_new != sub_need) st.sub_need[env] = sub_need_new;
-      reward[env] = (float)r;
-      if (reward64) reward64[env] = r;
-      terminated[env] = term ? 1 : 0;
-      fx_write_scalars(P, e, total_bars, last_price, obs_row);
+      reward[FX_OUT_IDX()] = (float)r;
+      if (reward64) reward64[FX_OUT_IDX()] = r;
+      terminated[FX_OUT_IDX()] = term ? 1 : 0;
+      fx_write_scalars(P, e, total_bars, last_price, FX_OBS_ROW());
     }
   } else if (lane == 0) {  // timing experiment only (FXENV_DEBUG & 2): cursor only
-    st.t[env] = t; st.flags[env] = flags; st.bar_index[env] = t + 1; reward[env] = 0.f; terminated[env] = 0;
+    st.t[env] = t; st.flags[env] = flags; st.bar_index[env] = t + 1; reward[FX_OUT_IDX()] = 0.f; terminated[FX_OUT_IDX()] = 0;
   }
   FX_STAMP(8);  // scalars written back
 
@@ -735,11 +739,13 @@ __device__ __forceinline__ void fx_step_env(const FxKernelParams& P, const void*
   __syncwarp();
   if (!(dbg & 1)) {
     fx_window_wait(ws, phase);
-    fx_emit_windows<FAST5>(P, lane, s_obs, scale, ws.win + win_shift, ws.stat, obs_row);
+    fx_emit_windows<FAST5>(P, lane, s_obs, scale, ws.win + win_shift, ws.stat, FX_OBS_ROW());
   }
   if (lane < 5 && !(dbg & 2)) st.nbar[(int64_t)env * 6 + lane] = nbar_next;
   FX_STAMP(9);
   FX_STAMP_GLOBAL(11);
+#undef FX_OBS_ROW
+#undef FX_OUT_IDX
 #undef FX_STAMP
 #undef FX_STAMP_DEP
 #undef FX_STAMP_GLOBAL
@@ -815,8 +821,8 @@ fx_rollout_kernel(const __grid_constant__ FxKernelParams P, const char* __restri
       if (lane == 0) { while (fx_ld_acquire(P.seq + env) != (int)k) __nanosleep(32); }
       __syncwarp();
     }
-    fx_step_env<STRAT, REWARD, FAST5>(P, actions + (size_t)k * N * 4, obs + (size_t)(k % (unsigned)obs_slots) * N * P.obs_dim,
-                                      reward + (size_t)k * N, nullptr, terminated + (size_t)k * N, (int)env, lane, ws, phase);
+    fx_step_env<STRAT, REWARD, FAST5>(P, actions, obs, reward, nullptr, terminated, (int)env, lane, ws, phase, k * N,
+                                      (k % (unsigned)obs_slots) * N);
     __syncwarp();
     if (lane == 0) fx_st_release(P.seq + env, (int)k + 1);
     g = __shfl_sync(FX_FULL, g_next, 0);
