@@ -138,6 +138,8 @@ int fxenv_abi_version(void) { return FXENV_ABI_VERSION; }
 
 const char* fxenv_last_error(const FxEnv* env) { return env ? env->err.c_str() : g_create_error.c_str(); }
 
+int fxenv_destroy(FxEnv* env);
+
 int fxenv_create(const FxConfig* cfg, FxEnv** out) {
   if (!cfg || !out) return fail(nullptr, FXENV_E_INVALID, "null argument");
   *out = nullptr;
@@ -176,7 +178,7 @@ int fxenv_create(const FxConfig* cfg, FxEnv** out) {
   ce = fx_configure_kernels(env->P);
   if (const char* rb = getenv("FXENV_ROLLOUT_BLOCKS"))  // timing experiments only: grid of the persistent launch
     if (atoi(rb) > 0 && atoi(rb) < env->P.resident_blocks) env->P.resident_blocks = atoi(rb);
-  if (ce != cudaSuccess) { delete env; return cuda_fail(nullptr, ce, "window_size * n_cols too large for shared memory"); }
+  if (ce != cudaSuccess) { fxenv_destroy(env); return cuda_fail(nullptr, ce, "window_size * n_cols too large for shared memory"); }
   // one slab for the whole per-env state (snapshot == one memcpy)
   const size_t N = (size_t)c.num_envs;
   const size_t ring = (c.reward == FX_REWARD_SHARPE) ? (size_t)c.sharpe_window : 1;
@@ -196,10 +198,10 @@ int fxenv_create(const FxConfig* cfg, FxEnv** out) {
   o_sz = plan.add(N * capP * 8);
   env->slab_bytes = plan.bytes;
   ce = cudaMalloc(&env->slab, plan.bytes);
-  if (ce != cudaSuccess) { delete env; return cuda_fail(nullptr, ce, "cudaMalloc(state slab)"); }
+  if (ce != cudaSuccess) { fxenv_destroy(env); return cuda_fail(nullptr, ce, "cudaMalloc(state slab)"); }
   cudaMemset(env->slab, 0, plan.bytes);
   ce = cudaMalloc(&env->P.seq, (N + 1) * sizeof(int32_t));
-  if (ce != cudaSuccess) { delete env; return cuda_fail(nullptr, ce, "cudaMalloc(seq)"); }
+  if (ce != cudaSuccess) { fxenv_destroy(env); return cuda_fail(nullptr, ce, "cudaMalloc(seq)"); }  // frees what was allocated so far
   cudaMemset(env->P.seq, 0, (N + 1) * sizeof(int32_t));
   FxDeviceState& st = env->P.st;
   unsigned char* b = env->slab;
