@@ -35,9 +35,8 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for _p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "golden")):
-    if _p not in sys.path:
-        sys.path.insert(0, _p)
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 
 OHLCV = ["OPEN", "HIGH", "LOW", "CLOSE", "VOLUME"]
 DEFAULTS = {"initial_cash": 10000.0, "position_size": 1.0, "commission": 0.0, "slippage": 0.0, "price_column": "CLOSE"}
@@ -53,22 +52,25 @@ L2_BYTES = 126 * 1024 * 1024
 ORDER_CAP = int(os.environ.get("FXENV_ORDER_CAP", "256"))  # order-table entries per env (overflowing envs are reported)
 
 
-def build_workload(name, envs_override=None):
-    import scenarios as S
+def build_workload(name, envs_per_gpu=None, n_shards=1):
+    """-> (cfg for envs_per_gpu * n_shards envs, candles, minutes, envs_per_gpu, obs_dim, algorithmic bytes per env-step,
+    description).  n_shards > 1 only for the CPU arm, which steps the envs of all N GPUs in one process."""
     from gym_fx_b200.config import lower_config
+    from gym_fx_b200.plugin_loader import DEFAULT_PLUGINS, build_plugins
     from gym_fx_b200.synth import PAIR_PIP, synth_candles, synth_minutes
 
     envs, W, strat, rew, pairs, R = WORKLOADS[name]
     W = int(os.environ.get("FXENV_BENCH_WINDOW", W))  # experiments only
-    if envs_override:
-        envs = envs_override
+    if envs_per_gpu:
+        envs = envs_per_gpu
     cfgd = {**DEFAULTS, "window_size": W, "feature_columns": list(OHLCV)}
-    pl = S.build_mirror_plugins(cfgd, {**S.DEFAULT_PLUGINS, "strategy": strat, "reward": rew,
-                                       "preprocessor": "feature_window_preprocessor"})
+    pl = build_plugins(cfgd, {**DEFAULT_PLUGINS, "strategy": strat, "reward": rew,
+                              "preprocessor": "feature_window_preprocessor"})
     cfg = lower_config(cfgd, broker_plugin=pl["broker"], strategy_plugin=pl["strategy"],
                        preprocessor_plugin=pl["preprocessor"], reward_plugin=pl["reward"], columns=OHLCV,
-                       num_envs=envs, num_pairs=pairs, order_capacity=ORDER_CAP,
+                       num_envs=envs * n_shards, num_pairs=pairs, order_capacity=ORDER_CAP,
                        pair_pip_size=list(PAIR_PIP[:pairs]) if pairs > 1 else None)
+    cfg.auto_reset = 1   # SURVEY 8d: auto-reset on (episodes span the table, so `terminated_frac` stays 0 in a run)
     candles = [synth_candles(T_BARS, p) for p in range(pairs)]
     minutes = [synth_minutes(T_BARS) for _ in range(pairs)]
     D = W * 5 + 2 * W + 4
@@ -76,6 +78,37 @@ def build_workload(name, envs_override=None):
     desc = (f"{name}: {envs} envs/GPU, feature_window W={W} F=5 rolling_zscore S=256, {strat}, {rew}, "
             f"{pairs} pair(s), synthetic 1-min candles T=2^19")
     return cfg, candles, minutes, envs, D, algo_bytes, desc
+
+
+def common_config(desc, envs_per_gpu, D, world):
+    """The `config` object of the JSON line: identical for both arms (`--impl ours` / `--impl reference`) of one run."""
+    return {"workload": desc, "envs_per_gpu": envs_per_gpu, "obs_dim": D, "parallelism": f"env-shard x{world}",
+            "actions": "uniform {0,1,2}, i.i.d. per env-step, seeded", "auto_reset": True}
+
+
+def pin_to_gpu_numa_node(local_rank):
+    """Bind this process (and therefore the pinned host buffers it allocates afterwards: first touch) to the CPU cores
+    of the NUMA node its GPU hangs off, so that host<->device copies of different ranks do not cross the socket link."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        dev = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.extend(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return {"numa_node": node, "cpus": len(allowed)}
+    except Exception:
+        return None
+    return None
 
 
 class ClockSampler:
@@ -200,14 +233,18 @@ def run_reference(args, rank, world):
     threads = os.cpu_count() or 1
     envs_per_gpu = args.envs or WORKLOADS[args.workload][0]
     total = envs_per_gpu * args.gpus
-    rate, done, dt, used, desc = cpu_port_rate(args.workload, total, args.steps, args.warmup, threads)
+    rate, done, dt, used, _ = cpu_port_rate(args.workload, total, args.steps, args.warmup, threads)
+    _, _, _, _, D, _, desc = build_workload(args.workload, envs_per_gpu)
     line = {
         "impl": "reference", "metric": "env-steps/sec", "value": rate, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": done, "warmup": args.warmup, "ms_per_step": dt / done * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "total_envs": total,
-                   "note": "CPU arm: C port of the reference path (oracle/fxenv_oracle.c); the Python reference "
-                           "(measured in the build container over the backtrader shim: 676 steps/s/process at this shape, profiles/r1_reference_python_rate.json) cannot travel to the GPU box"},
+        "config": common_config(desc, envs_per_gpu, D, args.gpus),
+        "details": {"total_envs": total,
+                    "note": "CPU arm: C port of the reference path (oracle/fxenv_oracle.c) stepping the envs of all "
+                            f"{args.gpus} GPU shard(s) on this host; the Python reference (measured in the build container "
+                            "over the backtrader shim: 676 steps/s/process at this shape, "
+                            "profiles/r1_reference_python_rate.json) cannot travel to the GPU box"},
         "cpu_baseline": {"value": rate, "unit": "env-steps/s", "cores": used, "kind": "port",
                          "sample": f"{total} envs x {done} steps, {used} host threads (pthreads), each thread runs its env slice without a per-step barrier"},
         "e2e": {"value": rate, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -258,9 +295,9 @@ def run_ours(args, rank, world, local_rank):
         import torch.distributed as dist_
         dist = dist_
         dist.init_process_group("nccl", device_id=dev)
+    numa = pin_to_gpu_numa_node(local_rank)
     cfg, candles, minutes, N, D, algo_bytes, desc = build_workload(args.workload, args.envs)
     K, Wm = args.steps, max(3, args.warmup)
-    cfg.auto_reset = 1   # auto-reset on (episodes span the table, so `terminated_frac` stays 0 in a run)
     env = VecFxEnv(cfg, candles, minutes, device=dev)
     # envs are sharded by rank: global env id = rank * N + i (no collective in the data path)
     check_pair_alignment(N, cfg.num_pairs)
@@ -276,12 +313,17 @@ def run_ours(args, rank, world, local_rank):
     terms = torch.empty((chunk, N), dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream(dev)
 
+    # the argument sets are validated once; a launch is then a single C call (VecFxEnv.plan_step_many)
+    full = env.plan_step_many(acts, ring, rews, terms)
+    rem = K % chunk
+    tail = env.plan_step_many(acts[:rem], ring, rews[:rem], terms[:rem]) if rem else None
+
     # warm-up (also instantiates the graph)
     wchunks = -(-Wm // chunk)
     for _ in range(max(1, wchunks)):
-        env.step_many(acts, ring, rews, terms)
-    if K % chunk:                            # the remainder batch has its own launch sequence: instantiate it now too
-        env.step_many(acts[:K % chunk], ring, rews[:K % chunk], terms[:K % chunk])
+        full()
+    if tail:                                 # the remainder batch has its own launch sequence: instantiate it now too
+        tail()
     torch.cuda.synchronize(dev)
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -290,12 +332,12 @@ def run_ours(args, rank, world, local_rank):
         dist.barrier()
     torch.cuda.synchronize(dev)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nfull = K // chunk
     ev0.record(stream)
-    for _ in range(K // chunk):
-        env.step_many(acts, ring, rews, terms)
-    if K % chunk:
-        r = K % chunk
-        env.step_many(acts[:r], ring, rews[:r], terms[:r])
+    for _ in range(nfull):
+        full()
+    if tail:
+        tail()
     ev1.record(stream)
     torch.cuda.synchronize(dev)
     if dist:
@@ -311,8 +353,8 @@ def run_ours(args, rank, world, local_rank):
     overflow = int((env.info()["flags"] & 16).ne(0).sum().item())
     term_frac = float(terms.float().mean().item())
 
-    # ---- e2e: reference-facing host-buffer call, copies inside the timed region
-    Ke = min(K, 200)
+    # ---- e2e: reference-facing host-buffer call, copies inside the timed region; median of 5 repeats of K steps
+    Ke, reps = min(K, 400), 5
     h_act = torch.empty(N, dtype=torch.int32).pin_memory()
     h_acts_all = acts[:min(chunk, Ke)].cpu()
     h_obs = torch.empty((N, D), dtype=torch.float32).pin_memory()
@@ -321,19 +363,21 @@ def run_ours(args, rank, world, local_rank):
     for k in range(3):
         h_act.copy_(h_acts_all[k % h_acts_all.shape[0]])
         env.step_host(h_act, h_obs, h_rew, h_term)
+    e2e_times = []
+    for _ in range(reps):
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for k in range(Ke):
+            h_act.copy_(h_acts_all[k % h_acts_all.shape[0]])
+            env.step_host(h_act, h_obs, h_rew, h_term)   # synchronous: returns when the results are in host memory
+        e2e_times.append(time.perf_counter() - t0)
+    te = torch.tensor(e2e_times, dtype=torch.float64, device=dev)
     if dist:
-        dist.barrier()
-    torch.cuda.synchronize(dev)
-    t0 = time.perf_counter()
-    for k in range(Ke):
-        h_act.copy_(h_acts_all[k % h_acts_all.shape[0]])
-        env.step_host(h_act, h_obs, h_rew, h_term)   # synchronous: returns when the results are in host memory
-    torch.cuda.synchronize(dev)
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if dist:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_rate = N * world * Ke / float(te.item())
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)      # per repeat: the slowest rank
+    e2e_s = float(te.median().item())
+    e2e_rate = N * world * Ke / e2e_s
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
@@ -350,17 +394,17 @@ def run_ours(args, rank, world, local_rank):
             "metric": "env-steps/sec", "value": N * world * K / (ms_max * 1e-3), "unit": "env-steps/s",
             "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms_max / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": desc, "envs_per_gpu": N, "obs_dim": D, "parallelism": f"env-shard x{world}",
-                       "actions": "uniform {0,1,2}, torch.Generator(seed=1234+rank), pre-generated on device",
-                       "l2": f"obs rows rotate through a {slots}-slot ring ({slots * N * D * 4 / 2**20:.0f} MiB > 126 MiB L2)",
-                       "engine": (f"persistent launch: {chunk} steps per launch, warps pull (step, env) tickets, per-env dependencies"
-                                  if engine == "persistent" else f"CUDA graph of {chunk} single-step launches (programmatic dependent launch)"),
-                       "auto_reset": True, "order_overflow_envs": overflow,
-                       "terminated_frac": term_frac},
+            "config": common_config(desc, N, D, world),
+            "details": {"actions": "torch.Generator(seed=1234+rank), pre-generated on device",
+                        "l2": f"obs rows rotate through a {slots}-slot ring ({slots * N * D * 4 / 2**20:.0f} MiB > 126 MiB L2)",
+                        "engine": (f"persistent launch: {chunk} steps per launch, warps pull (step, env) tickets, per-env dependencies"
+                                   if engine == "persistent" else f"CUDA graph of {chunk} single-step launches (programmatic dependent launch)"),
+                        "order_overflow_envs": overflow, "terminated_frac": term_frac, "numa": numa},
             "clocks": clocks,
             "e2e": {"value": e2e_rate, "unit": "env-steps/s", "h2d_bytes_per_step": N * 4,
-                    "d2h_bytes_per_step": N * (D * 4 + 4 + 1), "steps": Ke,
-                    "note": "fxenv_step_host: pinned host buffers, synchronous per step (PCIe-bound)"},
+                    "d2h_bytes_per_step": N * (D * 4 + 4 + 1), "steps": Ke, "repeats": reps,
+                    "note": "fxenv_step_host: pinned host buffers, synchronous per step (PCIe-bound); median of the "
+                            "repeats, each the slowest rank"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "frac_of_nominal_8TBs": achieved / 8000.0,

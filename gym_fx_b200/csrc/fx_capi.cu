@@ -38,10 +38,14 @@ struct FxEnv {
   bool tame[FXENV_MAX_PAIRS] = {};
   bool was_reset = false;
   bool first_reset = true;
+  bool seq_tracked = true;         // fx_rollout_kernel's seq[] / ticket words hold (seq_base, ticket_base): no memset needed
+  unsigned seq_base = 0u, ticket_base = 0u;
   int64_t launches = 0;
   std::string err;
   // fxenv_step_host staging
-  cudaStream_t hstream = nullptr;
+  static constexpr int kHostSlices = 8;
+  cudaStream_t hstream = nullptr, hcopy = nullptr;
+  cudaEvent_t hev[kHostSlices] = {};
   void* h_actions = nullptr;
   float* h_obs = nullptr;
   float* h_reward = nullptr;
@@ -236,6 +240,8 @@ int fxenv_destroy(FxEnv* env) {
   cudaFree(env->P.timing);
   cudaFree(env->h_actions); cudaFree(env->h_obs); cudaFree(env->h_reward); cudaFree(env->h_term);
   if (env->hstream) cudaStreamDestroy(env->hstream);
+  if (env->hcopy) cudaStreamDestroy(env->hcopy);
+  for (auto& ev : env->hev) if (ev) cudaEventDestroy(ev);
   delete env;
   return FXENV_OK;
 }
@@ -357,7 +363,19 @@ int fxenv_step_many(FxEnv* env, int n_steps, const void* actions_dev, float* obs
   if (rollout) {
     if ((unsigned long long)N * (unsigned long long)n_steps >= (1ull << 31))
       return fail(env, FXENV_E_INVALID, "num_envs * n_steps must be < 2^31 per fxenv_step_many call");
-    FX_CUDA(env, fx_launch_rollout(env->P, actions_dev, obs_dev, obs_slots, reward_dev, terminated_dev, n_steps, stream));
+    // the per-env sequence words and the ticket counter are epoch-based: the host knows what they hold after every
+    // launch, so no memset is needed between batches.  Inside a stream capture (the launch may be replayed any number
+    // of times) that knowledge is lost: such launches, and every launch after one, zero the words first.
+    cudaStreamCaptureStatus rcs = cudaStreamCaptureStatusNone;
+    if (stream != nullptr) cudaStreamIsCapturing(stream, &rcs);
+    if (rcs != cudaStreamCaptureStatusNone) env->seq_tracked = false;
+    const bool tracked = env->seq_tracked;
+    FX_CUDA(env, fx_launch_rollout(env->P, actions_dev, obs_dev, obs_slots, reward_dev, terminated_dev, n_steps,
+                                   tracked ? env->seq_base : 0u, tracked ? env->ticket_base : 0u, !tracked, stream));
+    if (tracked) {
+      env->seq_base += (unsigned)n_steps;
+      env->ticket_base += (unsigned)(N * (size_t)n_steps) + (unsigned)(fx_rollout_blocks(env->P) * FX_WARPS);
+    }
     env->launches += 1;
     return FXENV_OK;
   }
@@ -402,19 +420,34 @@ int fxenv_step_host(FxEnv* env, const void* actions_host, float* obs_host, float
   const size_t N = (size_t)env->P.cfg.num_envs, D = (size_t)env->P.obs_dim;
   if (!env->hstream) {
     FX_CUDA(env, cudaStreamCreateWithFlags(&env->hstream, cudaStreamNonBlocking));
+    FX_CUDA(env, cudaStreamCreateWithFlags(&env->hcopy, cudaStreamNonBlocking));
+    for (auto& ev : env->hev) FX_CUDA(env, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     FX_CUDA(env, cudaMalloc(&env->h_actions, N * 4));
     FX_CUDA(env, cudaMalloc(&env->h_obs, N * D * 4));
     FX_CUDA(env, cudaMalloc(&env->h_reward, N * 4));
     FX_CUDA(env, cudaMalloc(&env->h_term, N));
   }
-  cudaStream_t s = env->hstream;
+  // The call is PCIe-bound (the observation rows: 3.6 KB per env).  The envs are stepped in up to 8 slices, slice i's
+  // rows travelling to the host (copy engine, second stream) while slice i + 1 is being computed, so that only the
+  // first slice's kernel time is exposed in front of the transfer.
+  cudaStream_t s = env->hstream, sc = env->hcopy;
+  int slices = (int)(N / 512);
+  if (slices < 1) slices = 1;
+  if (slices > FxEnv::kHostSlices) slices = FxEnv::kHostSlices;
+  const size_t per = ((N + slices - 1) / slices + 31) & ~(size_t)31;
   FX_CUDA(env, cudaMemcpyAsync(env->h_actions, actions_host, N * 4, cudaMemcpyHostToDevice, s));
-  FX_CUDA(env, fx_launch_step(env->P, env->h_actions, env->h_obs, env->h_reward, nullptr, env->h_term, s));
-  env->launches++;
-  FX_CUDA(env, cudaMemcpyAsync(obs_host, env->h_obs, N * D * 4, cudaMemcpyDeviceToHost, s));
-  FX_CUDA(env, cudaMemcpyAsync(reward_host, env->h_reward, N * 4, cudaMemcpyDeviceToHost, s));
-  FX_CUDA(env, cudaMemcpyAsync(terminated_host, env->h_term, N, cudaMemcpyDeviceToHost, s));
-  FX_CUDA(env, cudaStreamSynchronize(s));
+  for (int i = 0; i < slices; i++) {
+    const size_t e0 = (size_t)i * per, e1 = (e0 + per < N) ? e0 + per : N;
+    if (e0 >= e1) break;
+    FX_CUDA(env, fx_launch_step(env->P, env->h_actions, env->h_obs, env->h_reward, nullptr, env->h_term, s, (int)e0, (int)e1));
+    env->launches++;
+    FX_CUDA(env, cudaEventRecord(env->hev[i], s));
+    FX_CUDA(env, cudaStreamWaitEvent(sc, env->hev[i], 0));
+    FX_CUDA(env, cudaMemcpyAsync(obs_host + e0 * D, env->h_obs + e0 * D, (e1 - e0) * D * 4, cudaMemcpyDeviceToHost, sc));
+  }
+  FX_CUDA(env, cudaMemcpyAsync(reward_host, env->h_reward, N * 4, cudaMemcpyDeviceToHost, sc));
+  FX_CUDA(env, cudaMemcpyAsync(terminated_host, env->h_term, N, cudaMemcpyDeviceToHost, sc));
+  FX_CUDA(env, cudaStreamSynchronize(sc));  // sc's last copy waited for the last slice's kernel: s is idle too
   return FXENV_OK;
 }
 

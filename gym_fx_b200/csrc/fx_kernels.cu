@@ -265,10 +265,65 @@ __device__ __noinline__ void fx_emit_windows_t(const FxKernelParams& P, int lane
   }
 }
 
+// The BASELINE shape (F == n_cols == 5 identity columns, full window, W % 4 == 0, 16-byte aligned row, price window on):
+// 16-byte streaming stores.  A lane owns the float4 q = lane + 30 * it of the [W][5] block (30 lanes active): its four
+// features are (4 * (lane % 5) + i) % 5 in every iteration, so their scale factors stay in registers, and a z-score is
+// ONE fp64 fma, x * (1/std) + (-mean / std) (the reference computes (x - mean) / std in fp64 and casts to float32; the
+// difference is far below half a float32 ulp).  prices | returns: a lane owns 4 consecutive rows.
+template <bool CLIP, bool TAME>
+__device__ __noinline__ void fx_emit_fast5_q(const FxKernelParams& P, int lane, bool scale, const double* __restrict__ win,
+                                             const double* sstat, float* __restrict__ out) {
+  const FxConfig& c = P.cfg;
+  const int W = c.window_size;
+  const float clipf = (float)c.feature_clip;
+  if (lane < 30) {
+    const int j4 = (lane % 5) * 4;
+    double r[4], a[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int f = (j4 + i) % 5;
+      const bool z = scale && !c.feature_binary[f];
+      r[i] = z ? sstat[2 * f + 1] : 1.0;
+      a[i] = z ? -(sstat[2 * f] * r[i]) : 0.0;
+    }
+    const int nq = (5 * W) >> 2;
+    float4* __restrict__ o4 = reinterpret_cast<float4*>(out);
+#pragma unroll 1
+    for (int q = lane; q < nq; q += 30) {
+      const double* __restrict__ x = win + 4 * q;  // the staged span may start on an odd double: 8-byte loads
+      float4 v;
+      v.x = fx_finish_t<CLIP, TAME>((float)fma(x[0], r[0], a[0]), clipf);
+      v.y = fx_finish_t<CLIP, TAME>((float)fma(x[1], r[1], a[1]), clipf);
+      v.z = fx_finish_t<CLIP, TAME>((float)fma(x[2], r[2], a[2]), clipf);
+      v.w = fx_finish_t<CLIP, TAME>((float)fma(x[3], r[3], a[3]), clipf);
+      __stcs(o4 + q, v);
+    }
+  }
+  const int pc = c.price_col;
+  float* __restrict__ op = out + 5 * W;
+#pragma unroll 1
+  for (int w0 = 4 * lane; w0 < W; w0 += 128) {
+    const double* __restrict__ pr = win + w0 * 5 + pc;
+    const double pm = (w0 > 0) ? pr[-5] : pr[0];
+    const double p0 = pr[0], p1 = pr[5], p2 = pr[10], p3 = pr[15];
+    float4 pv, rv;
+    pv.x = (float)p0; pv.y = (float)p1; pv.z = (float)p2; pv.w = (float)p3;
+    rv.x = (w0 > 0) ? (float)(p0 - pm) : 0.0f; rv.y = (float)(p1 - p0); rv.z = (float)(p2 - p1); rv.w = (float)(p3 - p2);
+    __stcs(reinterpret_cast<float4*>(op + w0), pv);
+    __stcs(reinterpret_cast<float4*>(op + W + w0), rv);
+  }
+}
+
 template <bool FAST5>
 __device__ __forceinline__ void fx_emit_windows(const FxKernelParams& P, int lane, int s, bool scale,
                                                 const double* __restrict__ win, const double* sstat,
                                                 float* __restrict__ out) {
+  if (FAST5 && s >= P.cfg.window_size && (P.cfg.window_size & 3) == 0 && P.cfg.include_price_window &&
+      P.cfg.feature_clip > 0.0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    if (P.tame_data) fx_emit_fast5_q<true, true>(P, lane, scale, win, sstat, out);
+    else fx_emit_fast5_q<true, false>(P, lane, scale, win, sstat, out);
+    return;
+  }
   const bool lng = P.cfg.window_size >= 384;
   if (P.cfg.feature_clip > 0.0) {
     if (P.tame_data) {
@@ -767,12 +822,13 @@ __device__ __forceinline__ void fx_st_release(int32_t* p, int v) {
 template <int STRAT, int REWARD, bool FAST5>
 __global__ void __launch_bounds__(FX_WARPS * 32, FX_MIN_BLOCKS)
 fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict__ actions, float* __restrict__ obs,
-               float* __restrict__ reward, double* __restrict__ reward64, uint8_t* __restrict__ terminated) {
+               float* __restrict__ reward, double* __restrict__ reward64, uint8_t* __restrict__ terminated,
+               const int env_begin, const int env_end) {
   extern __shared__ __align__(16) unsigned char fx_smem[];
   const FxConfig& c = P.cfg;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int env = blockIdx.x * FX_WARPS + warp;
-  if (env >= c.num_envs) return;
+  const int env = env_begin + blockIdx.x * FX_WARPS + warp;  // a launch covers the envs [env_begin, env_end)
+  if (env >= env_end) return;
   const int ring_len = (REWARD == FX_REWARD_SHARPE) ? c.sharpe_window : 0;
   const int win_doubles = fx_window_doubles(c.window_size, c.n_cols);
   const WarpSmem ws = fx_carve(fx_smem + (size_t)warp * fx_warp_smem_bytes(win_doubles, ring_len), win_doubles, ring_len);
@@ -797,34 +853,40 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
 template <int STRAT, int REWARD, bool FAST5>
 __global__ void __launch_bounds__(FX_WARPS * 32, FX_ROLLOUT_MIN_BLOCKS)
 fx_rollout_kernel(const __grid_constant__ FxKernelParams P, const char* __restrict__ actions, float* __restrict__ obs,
-                  const int obs_slots, float* __restrict__ reward, uint8_t* __restrict__ terminated, const int n_steps) {
+                  const int obs_slots, float* __restrict__ reward, uint8_t* __restrict__ terminated, const int n_steps,
+                  const unsigned seq_base, const unsigned ticket_base) {
   extern __shared__ __align__(16) unsigned char fx_smem[];
   const FxConfig& c = P.cfg;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ring_len = (REWARD == FX_REWARD_SHARPE) ? c.sharpe_window : 0;
   const int win_doubles = fx_window_doubles(c.window_size, c.n_cols);
   const WarpSmem ws = fx_carve(fx_smem + (size_t)warp * fx_warp_smem_bytes(win_doubles, ring_len), win_doubles, ring_len);
+  asm volatile("griddepcontrol.launch_dependents;");  // the next batch's launch latency hides behind this one
   fx_window_init(lane, ws);
   const unsigned N = (unsigned)c.num_envs;
-  const unsigned long long total = (unsigned long long)N * (unsigned)n_steps;
+  const unsigned total = N * (unsigned)n_steps;  // < 2^31 (checked by the caller)
   unsigned* ticket = reinterpret_cast<unsigned*>(P.seq + N);
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // everything below touches memory the previous launch wrote
+  // seq[] and the ticket counter are never reset: this launch's values start at seq_base / ticket_base (kept by the
+  // host: every launch leaves seq[env] = seq_base + n_steps and the counter at ticket_base + total + #warps, because
+  // each warp draws exactly one ticket >= total).  Unsigned differences make the 2^32 wrap harmless.
   unsigned g = 0u;
-  if (lane == 0) g = atomicAdd(ticket, 1u);
+  if (lane == 0) g = atomicAdd(ticket, 1u) - ticket_base;
   g = __shfl_sync(FX_FULL, g, 0);
   unsigned phase = 0u;
   while (g < total) {
     // the ticket after this one is requested now: its atomic round trip hides behind the env-step
     unsigned g_next = 0u;
-    if (lane == 0) g_next = atomicAdd(ticket, 1u);
+    if (lane == 0) g_next = atomicAdd(ticket, 1u) - ticket_base;
     const unsigned k = g / N, env = g - k * N;
     if (k > 0u) {
-      if (lane == 0) { while (fx_ld_acquire(P.seq + env) != (int)k) __nanosleep(32); }
+      if (lane == 0) { while ((unsigned)fx_ld_acquire(P.seq + env) != seq_base + k) __nanosleep(32); }
       __syncwarp();
     }
     fx_step_env<STRAT, REWARD, FAST5>(P, actions, obs, reward, nullptr, terminated, (int)env, lane, ws, phase, k * N,
                                       (k % (unsigned)obs_slots) * N);
     __syncwarp();
-    if (lane == 0) fx_st_release(P.seq + env, (int)k + 1);
+    if (lane == 0) fx_st_release(P.seq + env, (int)(seq_base + k + 1u));
     g = __shfl_sync(FX_FULL, g_next, 0);
     phase++;
   }
@@ -912,7 +974,7 @@ __global__ void fx_stats_kernel(FxConfig c, const double* __restrict__ candles, 
   stats[idx * 2 + 1] = rc;
 }
 
-typedef void (*StepKernel)(const FxKernelParams, const void*, float*, float*, double*, uint8_t*);
+typedef void (*StepKernel)(const FxKernelParams, const void*, float*, float*, double*, uint8_t*, int, int);
 
 template <int STRAT>
 StepKernel pick_reward(int reward, bool fast5) {
@@ -932,7 +994,7 @@ StepKernel pick_kernel(const FxKernelParams& P) {
   }
 }
 
-typedef void (*RolloutKernel)(const FxKernelParams, const char*, float*, int, float*, uint8_t*, int);
+typedef void (*RolloutKernel)(const FxKernelParams, const char*, float*, int, float*, uint8_t*, int, unsigned, unsigned);
 
 template <int STRAT>
 RolloutKernel pick_rollout_reward(int reward, bool fast5) {
@@ -1000,9 +1062,10 @@ cudaError_t fx_configure_kernels(FxKernelParams& P) {
 }
 
 cudaError_t fx_launch_step(const FxKernelParams& P, const void* actions, float* obs, float* reward, double* reward64,
-                           uint8_t* terminated, cudaStream_t stream) {
+                           uint8_t* terminated, cudaStream_t stream, int env_begin, int env_end) {
+  if (env_end < 0) env_end = P.cfg.num_envs;
   cudaLaunchConfig_t lc = {};
-  lc.gridDim = dim3((P.cfg.num_envs + FX_WARPS - 1) / FX_WARPS);
+  lc.gridDim = dim3((env_end - env_begin + FX_WARPS - 1) / FX_WARPS);
   lc.blockDim = dim3(FX_WARPS * 32);
   lc.dynamicSmemBytes = step_smem_bytes(P);
   lc.stream = stream;
@@ -1011,19 +1074,37 @@ cudaError_t fx_launch_step(const FxKernelParams& P, const void* actions, float* 
   at[0].val.programmaticStreamSerializationAllowed = 1;
   lc.attrs = at;
   lc.numAttrs = (P.debug & 4) ? 0 : 1;  // FXENV_DEBUG & 4: plain stream-serialised launches (A/B timing only)
-  return cudaLaunchKernelEx(&lc, pick_kernel(P), P, actions, obs, reward, reward64, terminated);
+  return cudaLaunchKernelEx(&lc, pick_kernel(P), P, actions, obs, reward, reward64, terminated, env_begin, env_end);
 }
 
+int fx_rollout_blocks(const FxKernelParams& P) {
+  int blocks = (P.cfg.num_envs + FX_WARPS - 1) / FX_WARPS;
+  return blocks > P.resident_blocks ? P.resident_blocks : blocks;
+}
+
+// seq_base / ticket_base: the values seq[] and the ticket counter hold when this launch starts (see fx_rollout_kernel);
+// reset_words: zero them first with a stream-ordered memset (then both bases must be 0) -- used inside stream captures,
+// where the host cannot track what the counters will hold at replay time.
 cudaError_t fx_launch_rollout(const FxKernelParams& P, const void* actions, float* obs, int obs_slots, float* reward,
-                              uint8_t* terminated, int n_steps, cudaStream_t stream) {
+                              uint8_t* terminated, int n_steps, unsigned seq_base, unsigned ticket_base, bool reset_words,
+                              cudaStream_t stream) {
   const int N = P.cfg.num_envs;
-  cudaError_t e = cudaMemsetAsync(P.seq, 0, ((size_t)N + 1) * sizeof(int32_t), stream);
-  if (e != cudaSuccess) return e;
-  int blocks = (N + FX_WARPS - 1) / FX_WARPS;
-  if (blocks > P.resident_blocks) blocks = P.resident_blocks;
-  pick_rollout(P)<<<blocks, FX_WARPS * 32, step_smem_bytes(P), stream>>>(P, reinterpret_cast<const char*>(actions), obs, obs_slots,
-                                                                        reward, terminated, n_steps);
-  return cudaGetLastError();
+  if (reset_words) {
+    cudaError_t e = cudaMemsetAsync(P.seq, 0, ((size_t)N + 1) * sizeof(int32_t), stream);
+    if (e != cudaSuccess) return e;
+  }
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3(fx_rollout_blocks(P));
+  lc.blockDim = dim3(FX_WARPS * 32);
+  lc.dynamicSmemBytes = step_smem_bytes(P);
+  lc.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = at;
+  lc.numAttrs = (reset_words || (P.debug & 4)) ? 0 : 1;  // behind a memset node: plain stream order
+  return cudaLaunchKernelEx(&lc, pick_rollout(P), P, reinterpret_cast<const char*>(actions), obs, obs_slots, reward,
+                            terminated, n_steps, seq_base, ticket_base);
 }
 
 cudaError_t fx_launch_reset(const FxKernelParams& P, const int64_t* start_bar, const uint8_t* mask, int first,

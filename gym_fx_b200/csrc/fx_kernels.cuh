@@ -71,12 +71,15 @@ struct FxKernelParams {
 #endif
 
 // host-callable launchers (fx_kernels.cu)
+// one step of the envs [env_begin, env_end) (env_end < 0: all); the array arguments are the bases for env 0
 cudaError_t fx_launch_step(const FxKernelParams& P, const void* actions, float* obs, float* reward, double* reward64,
-                           uint8_t* terminated, cudaStream_t stream);
+                           uint8_t* terminated, cudaStream_t stream, int env_begin = 0, int env_end = -1);
 cudaError_t fx_launch_reset(const FxKernelParams& P, const int64_t* start_bar, const uint8_t* mask, int first,
                             cudaStream_t stream);
 cudaError_t fx_launch_observe(const FxKernelParams& P, float* obs, cudaStream_t stream);
 cudaError_t fx_launch_stats(const FxConfig& cfg, const double* candles, double* stats, int64_t T, cudaStream_t stream);
 cudaError_t fx_configure_kernels(FxKernelParams& P);
 cudaError_t fx_launch_rollout(const FxKernelParams& P, const void* actions, float* obs, int obs_slots, float* reward,
-                              uint8_t* terminated, int n_steps, cudaStream_t stream);
+                              uint8_t* terminated, int n_steps, unsigned seq_base, unsigned ticket_base, bool reset_words,
+                              cudaStream_t stream);
+int fx_rollout_blocks(const FxKernelParams& P);

@@ -40,3 +40,28 @@ def get_plugin_params(plugin_group: str, plugin_name: str):
         return load_plugin(plugin_group, plugin_name)[0].plugin_params
     except Exception as exc:
         raise ImportError(f"Failed to get plugin params for {plugin_name} from group {plugin_group}, Error: {exc}")
+
+
+# app/config.py:1-45 of the reference, only the keys the hot path reads (so that callers do not need the reference tree)
+DEFAULT_VALUES = {
+    "window_size": 32, "initial_cash": 10000.0, "position_size": 1.0, "commission": 0.0, "slippage": 0.0,
+    "price_column": "CLOSE", "date_column": "DATE_TIME", "headers": True, "max_rows": None,
+}
+
+DEFAULT_PLUGINS = dict(data_feed="default_data_feed", broker="default_broker", strategy="default_strategy",
+                       preprocessor="default_preprocessor", reward="pnl_reward", metrics="default_metrics")
+
+_GROUP_OF = {"data_feed": "data_feed.plugins", "broker": "broker.plugins", "strategy": "strategy.plugins",
+             "preprocessor": "preprocessor.plugins", "reward": "reward.plugins", "metrics": "metrics.plugins"}
+
+
+def build_plugins(config: dict, plugins: dict) -> dict:
+    """Instantiate one plugin per role the way the reference's driver does (app/main.py:20-24: `klass(config)` then
+    `set_params(**config)`).  `plugins` maps role (data_feed, broker, strategy, preprocessor, reward, metrics) -> name."""
+    out = {}
+    for role, name in plugins.items():
+        klass, _ = load_plugin(_GROUP_OF[role], name)
+        inst = klass(config)
+        inst.set_params(**config)
+        out[role] = inst
+    return out

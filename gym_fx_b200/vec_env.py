@@ -83,9 +83,13 @@ class VecFxEnv:
         """-> (obs [N, D] float32, info).  start_bars: int64 [N] first table row of each env's episode window."""
         sb = mk = None
         if start_bars is not None:
-            sb = torch.as_tensor(start_bars, dtype=torch.int64, device=self.device).contiguous()
+            sb = torch.as_tensor(start_bars, dtype=torch.int64, device=self.device).contiguous().reshape(-1)
+            if sb.numel() != self.num_envs:
+                raise ValueError(f"start_bars must have {self.num_envs} elements, got {sb.numel()}")
         if mask is not None:
-            mk = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+            mk = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous().reshape(-1)
+            if mk.numel() != self.num_envs:
+                raise ValueError(f"mask must have {self.num_envs} elements, got {mk.numel()}")
         rc = self.L.fxenv_reset(self._h, None if sb is None else sb.data_ptr(), None if mk is None else mk.data_ptr(),
                                 self._stream())
         _native.check(self.L, self._h, rc, "fxenv_reset")
@@ -102,25 +106,82 @@ class VecFxEnv:
         a = a.reshape(-1)
         if a.numel() != self.num_envs:
             raise ValueError(f"expected {self.num_envs} actions")
-        obs = self.obs if out_obs is None else out_obs
+        obs = self.obs
+        if out_obs is not None:
+            self._check("out_obs", out_obs, torch.float32, (self.num_envs, self.obs_dim))
+            obs = out_obs
         rc = self.L.fxenv_step(self._h, a.data_ptr(), obs.data_ptr(), self.reward.data_ptr(),
                                self.terminated.data_ptr(), self.reward64.data_ptr(), self._stream())
         _native.check(self.L, self._h, rc, "fxenv_step")
         return obs, self.reward, self.terminated.view(torch.bool), self.truncated, self.info()
 
+    # ---- argument checks of the raw-pointer calls: a wrong dtype / shape / device would be read as garbage or fault
+    def _check(self, name: str, t: torch.Tensor, dtype: torch.dtype, shape, host: bool = False):
+        if not isinstance(t, torch.Tensor):
+            raise TypeError(f"{name} must be a torch.Tensor")
+        if t.dtype != dtype:
+            raise ValueError(f"{name} must be {dtype}, got {t.dtype}")
+        if tuple(t.shape) != tuple(shape):
+            raise ValueError(f"{name} must have shape {tuple(shape)}, got {tuple(t.shape)}")
+        if not t.is_contiguous():
+            raise ValueError(f"{name} must be contiguous")
+        if host:
+            if t.device.type != "cpu":
+                raise ValueError(f"{name} must be a host (ideally pinned) tensor")
+        elif t.device != self.device:
+            raise ValueError(f"{name} must live on {self.device}, got {t.device}")
+
+    def _check_batch(self, actions, obs_ring, rewards, terminated):
+        if actions.dim() != 2:
+            raise ValueError("actions must be [K, num_envs]")
+        K, N, D = int(actions.shape[0]), self.num_envs, self.obs_dim
+        if K < 1:
+            raise ValueError("step_many needs at least one step")
+        self._check("actions", actions, self.action_dtype, (K, N))
+        if obs_ring.dim() != 3 or obs_ring.shape[0] < 1:
+            raise ValueError("obs_ring must be [slots, num_envs, obs_dim] with slots >= 1")
+        self._check("obs_ring", obs_ring, torch.float32, (int(obs_ring.shape[0]), N, D))
+        self._check("rewards", rewards, torch.float32, (K, N))
+        self._check("terminated", terminated, torch.uint8, (K, N))
+        return K
+
     def step_many(self, actions: torch.Tensor, obs_ring: torch.Tensor, rewards: torch.Tensor, terminated: torch.Tensor):
         """K consecutive steps with all actions supplied up front (replay / random / scripted drivers); identical results
-        to K calls of step().  actions [K, N]; obs_ring [slots, N, D] (step k writes slot k % slots); rewards float32
-        [K, N]; terminated uint8 [K, N].  The library runs the batch as one persistent launch or as a cached CUDA graph
-        of single steps (`step_many_engine`)."""
-        K = actions.shape[0]
-        rc = self.L.fxenv_step_many(self._h, int(K), actions.data_ptr(), obs_ring.data_ptr(), int(obs_ring.shape[0]),
+        to K calls of step().  actions [K, N] (int32, or float32 in continuous mode); obs_ring float32 [slots, N, D]
+        (step k writes slot k % slots); rewards float32 [K, N]; terminated uint8 [K, N].  The library runs the batch as one
+        persistent launch or as a cached CUDA graph of single steps (`step_many_engine`)."""
+        K = self._check_batch(actions, obs_ring, rewards, terminated)
+        rc = self.L.fxenv_step_many(self._h, K, actions.data_ptr(), obs_ring.data_ptr(), int(obs_ring.shape[0]),
                                     rewards.data_ptr(), terminated.data_ptr(), self._stream())
         _native.check(self.L, self._h, rc, "fxenv_step_many")
+
+    def plan_step_many(self, actions: torch.Tensor, obs_ring: torch.Tensor, rewards: torch.Tensor,
+                       terminated: torch.Tensor):
+        """Validate a step_many argument set ONCE and return a zero-argument callable that enqueues the batch on the
+        current stream with a single C call (for loops that replay the same buffers: the checks and the Python attribute
+        lookups stay out of the hot loop).  The tensors must stay alive and unchanged in place while the plan is used."""
+        K = self._check_batch(actions, obs_ring, rewards, terminated)
+        fn, h, check = self.L.fxenv_step_many, self._h, _native.check
+        args = (K, actions.data_ptr(), obs_ring.data_ptr(), int(obs_ring.shape[0]), rewards.data_ptr(),
+                terminated.data_ptr())
+        keep = (actions, obs_ring, rewards, terminated)
+        stream_of = self._stream
+
+        def launch(_keep=keep):
+            rc = fn(h, *args, stream_of())
+            if rc:
+                check(self.L, h, rc, "fxenv_step_many")
+
+        return launch
 
     def step_host(self, actions_host: torch.Tensor, obs_host: torch.Tensor, reward_host: torch.Tensor,
                   terminated_host: torch.Tensor):
         """Reference-facing call with (pinned) HOST tensors: H2D actions, one step, D2H results, synchronous."""
+        N, D = self.num_envs, self.obs_dim
+        self._check("actions_host", actions_host, self.action_dtype, (N,), host=True)
+        self._check("obs_host", obs_host, torch.float32, (N, D), host=True)
+        self._check("reward_host", reward_host, torch.float32, (N,), host=True)
+        self._check("terminated_host", terminated_host, torch.uint8, (N,), host=True)
         rc = self.L.fxenv_step_host(self._h, actions_host.data_ptr(), obs_host.data_ptr(), reward_host.data_ptr(),
                                     terminated_host.data_ptr())
         _native.check(self.L, self._h, rc, "fxenv_step_host")

@@ -159,12 +159,6 @@ def full_config(sc):
 
 def build_mirror_plugins(cfg, plugins):
     """Instantiate this package's plugin mirrors the way app/main.py:20-24 instantiates the reference's."""
-    import importlib
+    from gym_fx_b200.plugin_loader import build_plugins
 
-    out = {}
-    for group, name in plugins.items():
-        mod = importlib.import_module(f"gym_fx_b200.{group}_plugins.{name}")
-        inst = mod.Plugin(cfg)
-        inst.set_params(**cfg)
-        out[group] = inst
-    return out
+    return build_plugins(cfg, plugins)
