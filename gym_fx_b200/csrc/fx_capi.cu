@@ -179,6 +179,8 @@ int fxenv_create(const FxConfig* cfg, FxEnv** out) {
     env->P.fast_features = 5;
     for (int i = 0; i < 5; i++) if (c.feature_cols[i] != i) env->P.fast_features = 0;
   }
+  env->P.stagger_ns = 300;
+  if (const char* sv = getenv("FXENV_STAGGER_NS")) env->P.stagger_ns = atoi(sv);  // timing experiments only
   ce = fx_configure_kernels(env->P);
   if (const char* rb = getenv("FXENV_ROLLOUT_BLOCKS"))  // timing experiments only: grid of the persistent launch
     if (atoi(rb) > 0 && atoi(rb) < env->P.resident_blocks) env->P.resident_blocks = atoi(rb);
@@ -431,7 +433,9 @@ int fxenv_step_host(FxEnv* env, const void* actions_host, float* obs_host, float
   // rows travelling to the host (copy engine, second stream) while slice i + 1 is being computed, so that only the
   // first slice's kernel time is exposed in front of the transfer.
   cudaStream_t s = env->hstream, sc = env->hcopy;
-  int slices = (int)(N / 512);
+  int slices = (int)(N / 1024);
+  if (slices > 2) slices = 2;  // measured (cfg2, 4096 envs): 1 slice 13.0 M env-steps/s, 8 slices 12.6 M (every extra DMA costs)
+  if (const char* hs = getenv("FXENV_HOST_SLICES")) slices = atoi(hs);  // timing experiments only
   if (slices < 1) slices = 1;
   if (slices > FxEnv::kHostSlices) slices = FxEnv::kHostSlices;
   const size_t per = ((N + slices - 1) / slices + 31) & ~(size_t)31;

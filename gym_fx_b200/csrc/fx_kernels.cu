@@ -28,6 +28,9 @@
 #include "fx_kernels.cuh"
 
 #define FX_FULL 0xffffffffu
+#ifndef FX_EMIT_EARLY
+#define FX_EMIT_EARLY 1  // emit the observation windows right after the order sweep (see FX_EMIT_OBSERVATION)
+#endif
 
 namespace {
 
@@ -72,6 +75,9 @@ __device__ __forceinline__ int fx_window_issue(const FxPairTable& tb, int C, int
   const int shift = (int)(e0 & 1);
   const unsigned bytes = (unsigned)(((have * C + shift + 1) & ~1) * 8);
   if (lane == 0) {
+    // a persistent warp reuses this buffer: its previous env-step may have written ws.stat with ordinary stores (warm-up
+    // statistics) -- order them before the bulk copies (async proxy) that overwrite the same bytes
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     const unsigned bar_a = (unsigned)__cvta_generic_to_shared(ws.bar);
     const unsigned dst_a = (unsigned)__cvta_generic_to_shared(ws.win);
     const unsigned sbytes = stats_row ? (unsigned)n_features * 16u : 0u;  // {mean, 1/std} rows are 16-byte multiples
@@ -579,6 +585,34 @@ __device__ __forceinline__ void fx_step_env(const FxKernelParams& P, const void*
 
   FX_STAMP_DEP(1, __double_as_longlong(b.o) + __double_as_longlong(b.c));  // the new bar has arrived
 
+  // ---- observation windows (app/env.py:160 -> preprocessor.make_observation) from the staged copy.  They depend on
+  // the bar cursor only (not on what the broker / strategy did), so they are emitted right after the order sweep
+  // (FX_EMIT_EARLY): the row's streaming stores then drain while the strategy / reward / write-back run, and the release
+  // fence that publishes the env-step to the next warp (fx_rollout_kernel) finds nothing left to wait for.
+  // Running z-score statistics while the history window is still growing (or expanding_zscore): warm-up path, one
+  // extra round trip here instead of registers held across the broker pass.
+#define FX_EMIT_OBSERVATION()                                                                              \
+  do {                                                                                                     \
+    if (lane < c.n_features && (welford_live || (scale && !table_stats))) {                                \
+      const int64_t wi = ((int64_t)env * FXENV_MAX_FEATURES + lane) * 2;                                   \
+      double wf_m = st.welford[wi], wf_m2 = st.welford[wi + 1];                                            \
+      if (welford_live) {                                                                                  \
+        fx_welford_add(wf_m, wf_m2, row[c.feature_cols[lane]], t + 1);                                     \
+        st.welford[wi] = wf_m; st.welford[wi + 1] = wf_m2;                                                 \
+      }                                                                                                    \
+      if (scale && !table_stats) {                                                                         \
+        double st_m, st_r;                                                                                 \
+        fx_welford_to_stats(wf_m, wf_m2, hn, st_m, st_r);                                                  \
+        ws.stat[2 * lane] = st_m; ws.stat[2 * lane + 1] = st_r;                                            \
+      }                                                                                                    \
+    }                                                                                                      \
+    __syncwarp();                                                                                          \
+    if (!(dbg & 1)) {                                                                                      \
+      fx_window_wait(ws, phase);                                                                           \
+      fx_emit_windows<FAST5>(P, lane, s_obs, scale, ws.win + win_shift, ws.stat, FX_OBS_ROW());            \
+    }                                                                                                      \
+  } while (0)
+
   double nbar_next = 0.0;
   if (!(dbg & 2)) {
     int n_live = n;
@@ -665,11 +699,14 @@ __device__ __forceinline__ void fx_step_env(const FxKernelParams& P, const void*
       fx_mark_to_market(c, e, b.c);
     }
     FX_STAMP(5);  // broker pass done, marked to market
-    // candle of the next call (lanes 0..4): requested now, stored after the observation has been emitted
+    // candle of the next call (lanes 0..4): requested now, stored at the end of the env-step
     if (lane < 5) {
       const int tn = (t + 1 < total_bars) ? t + 1 : total_bars - 1;
       nbar_next = tb.candles[(start + tn) * (int64_t)C + (lane < 4 ? lane : c.price_col)];
     }
+#if FX_EMIT_EARLY
+    FX_EMIT_OBSERVATION();
+#endif
 
     double r;
     int n_final = n_live, n_acc_new = n_live;
@@ -770,35 +807,21 @@ __device__ __forceinline__ void fx_step_env(const FxKernelParams& P, const void*
       terminated[FX_OUT_IDX()] = term ? 1 : 0;
       fx_write_scalars(P, e, total_bars, last_price, FX_OBS_ROW());
     }
-  } else if (lane == 0) {  // timing experiment only (FXENV_DEBUG & 2): cursor only
-    st.t[env] = t; st.flags[env] = flags; st.bar_index[env] = t + 1; reward[FX_OUT_IDX()] = 0.f; terminated[FX_OUT_IDX()] = 0;
+  } else {  // timing experiment only (FXENV_DEBUG & 2): cursor only
+    if (lane == 0) { st.t[env] = t; st.flags[env] = flags; st.bar_index[env] = t + 1; reward[FX_OUT_IDX()] = 0.f; terminated[FX_OUT_IDX()] = 0; }
+#if FX_EMIT_EARLY
+    FX_EMIT_OBSERVATION();
+#endif
   }
   FX_STAMP(8);  // scalars written back
 
-  // ---- observation windows (app/env.py:160 -> preprocessor.make_observation) from the staged copy
-  // running z-score statistics while the history window is still growing (or expanding_zscore): warm-up path, one
-  // extra round trip here instead of registers held across the broker pass
-  if (lane < c.n_features && (welford_live || (scale && !table_stats))) {
-    const int64_t wi = ((int64_t)env * FXENV_MAX_FEATURES + lane) * 2;
-    double wf_m = st.welford[wi], wf_m2 = st.welford[wi + 1];
-    if (welford_live) {
-      fx_welford_add(wf_m, wf_m2, row[c.feature_cols[lane]], t + 1);
-      st.welford[wi] = wf_m; st.welford[wi + 1] = wf_m2;
-    }
-    if (scale && !table_stats) {
-      double st_m, st_r;
-      fx_welford_to_stats(wf_m, wf_m2, hn, st_m, st_r);
-      ws.stat[2 * lane] = st_m; ws.stat[2 * lane + 1] = st_r;
-    }
-  }
-  __syncwarp();
-  if (!(dbg & 1)) {
-    fx_window_wait(ws, phase);
-    fx_emit_windows<FAST5>(P, lane, s_obs, scale, ws.win + win_shift, ws.stat, FX_OBS_ROW());
-  }
+#if !FX_EMIT_EARLY
+  FX_EMIT_OBSERVATION();
+#endif
   if (lane < 5 && !(dbg & 2)) st.nbar[(int64_t)env * 6 + lane] = nbar_next;
   FX_STAMP(9);
   FX_STAMP_GLOBAL(11);
+#undef FX_EMIT_OBSERVATION
 #undef FX_OBS_ROW
 #undef FX_OUT_IDX
 #undef FX_STAMP
@@ -867,6 +890,10 @@ fx_rollout_kernel(const __grid_constant__ FxKernelParams P, const char* __restri
   const unsigned total = N * (unsigned)n_steps;  // < 2^31 (checked by the caller)
   unsigned* ticket = reinterpret_cast<unsigned*>(P.seq + N);
   asm volatile("griddepcontrol.wait;" ::: "memory");  // everything below touches memory the previous launch wrote
+  // All warps of the grid start at the same instant and would walk through the phases of their first env-steps in
+  // lockstep (every warp loading, then every warp sweeping, then every warp storing its row).  Spreading the start of the
+  // warps that share an SM over about one env-step de-phases them from the first step on.
+  if (P.stagger_ns > 0) __nanosleep((blockIdx.x / (unsigned)P.num_sms) * (unsigned)P.stagger_ns);
   // seq[] and the ticket counter are never reset: this launch's values start at seq_base / ticket_base (kept by the
   // host: every launch leaves seq[env] = seq_base + n_steps and the counter at ticket_base + total + #warps, because
   // each warp draws exactly one ticket >= total).  Unsigned differences make the 2^32 wrap harmless.
@@ -1052,6 +1079,7 @@ cudaError_t fx_configure_kernels(FxKernelParams& P) {
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    P.num_sms = sms > 0 ? sms : 1;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_rollout(P), FX_WARPS * 32, smem);
     if (e != cudaSuccess) return e;
     P.resident_blocks = sms * per_sm;

@@ -81,6 +81,8 @@ class GymFxEnv(spaces.EnvBase):
 
         self._vec: Optional[VecFxEnv] = None
         self._started = False
+        self._terminated = False
+        self._last_equity = self.initial_cash   # bridge.equity survives close() in the reference (app/env.py:258-262)
         self._np_random = np.random.default_rng()
 
     # ------------------------------------------------------------------ Gymnasium API
@@ -95,19 +97,26 @@ class GymFxEnv(spaces.EnvBase):
             self._vec = VecFxEnv(self._fxcfg, [self._table], [self._minutes])
         obs, _ = self._vec.reset(torch.zeros(1, dtype=torch.int64))
         self._started = True
+        self._terminated = False
         info = self._make_info()
         info.pop("_pnl")
+        self._last_equity = info["equity"]
         return self._split(obs.cpu().numpy()[0]), info
 
     def step(self, action):
         if not self._started:
             raise RuntimeError("Call reset() before step().")
+        was_terminated = self._terminated
         a = torch.tensor([self._host_action(action)], dtype=self._vec.action_dtype, device=self._vec.device)
         obs, _, term, _, _ = self._vec.step(a)
         reward = float(self._vec.reward64[0])          # fp64, like the reference's Python float
         terminated = bool(term[0])
+        self._terminated = terminated
         info = self._make_info()
-        info.update(reward=reward, pnl=info.pop("_pnl"), trade_cost=0.0)  # trade_cost is always 0.0 (App. B #7)
+        pnl = info.pop("_pnl")
+        self._last_equity = info["equity"]
+        if not was_terminated:  # a step on an already terminated env returns the bare _make_info() (app/env.py:137-138)
+            info.update(reward=reward, pnl=pnl, trade_cost=0.0)  # trade_cost is always 0.0 (App. B #7)
         return self._split(obs[0].cpu().numpy()), reward, terminated, False, info
 
     def render(self):
@@ -144,6 +153,6 @@ class GymFxEnv(spaces.EnvBase):
                 "commission_paid": float(i["commission_paid"][0]), "_pnl": eq - prev}
 
     def summary(self) -> Dict[str, Any]:
-        final = float(self._vec.info()["equity"][0]) if self._vec is not None else self.initial_cash
+        final = float(self._vec.info()["equity"][0]) if self._vec is not None else self._last_equity
         return self.metrics_plugin.summarize(initial_cash=self.initial_cash, final_equity=final, analyzers={},
                                              config=self.config)

@@ -66,6 +66,9 @@ class VecFxEnv:
     # ------------------------------------------------------------------ lifecycle
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
+            # the info tensors are zero-copy views of the library's state slab, which fxenv_destroy frees: drop the cached
+            # ones (views a caller still holds become invalid, like any tensor handed out by info() -- clone to keep)
+            self._info_views.clear()
             self.L.fxenv_destroy(self._h)
             self._h = C.c_void_p()
 
