@@ -29,7 +29,11 @@ class FxEnvError(RuntimeError):
 class FxInfoPtrs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "equity", "prev_equity", "price", "cash", "position_size", "position_price", "commission_paid",
-        "position", "bar_index", "total_bars", "trades", "n_orders", "flags")]
+        "position", "bar_index", "total_bars", "trades", "n_orders", "flags", "run_stats")]
+
+RUN_STATS = 12  # FXENV_RUN_STATS
+RS = {"dd_maxvalue": 0, "dd_max_money": 1, "dd_max_pct": 2, "tr_pnl": 3, "tr_comm": 4, "tr_price": 5, "pnl_net": 6,
+      "sqn_mean": 7, "sqn_m2": 8, "opened": 9, "won": 10, "lost": 11}  # FXENV_RS_*
 
 
 INFO_DTYPES = {
@@ -89,7 +93,7 @@ def load():
     L.fxenv_launch_count.argtypes = [vp]
     L.fxenv_step_many_engine.restype = C.c_int
     L.fxenv_step_many_engine.argtypes = [vp, C.c_int]
-    if L.fxenv_abi_version() != 1:
+    if L.fxenv_abi_version() != 2:
         raise FxEnvError("libfxenv.so ABI version mismatch")
     _lib = L
     return L

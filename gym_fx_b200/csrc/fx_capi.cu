@@ -38,6 +38,7 @@ struct FxEnv {
   bool tame[FXENV_MAX_PAIRS] = {};
   bool was_reset = false;
   bool first_reset = true;
+  int timeline_steps = 0;
   bool seq_tracked = true;         // fx_rollout_kernel's seq[] / ticket words hold (seq_base, ticket_base): no memset needed
   unsigned seq_base = 0u, ticket_base = 0u;
   int64_t launches = 0;
@@ -179,8 +180,14 @@ int fxenv_create(const FxConfig* cfg, FxEnv** out) {
     env->P.fast_features = 5;
     for (int i = 0; i < 5; i++) if (c.feature_cols[i] != i) env->P.fast_features = 0;
   }
-  env->P.stagger_ns = 300;
-  if (const char* sv = getenv("FXENV_STAGGER_NS")) env->P.stagger_ns = atoi(sv);  // timing experiments only
+  if (const char* tl = getenv("FXENV_TIMELINE")) {  // debug, timing build: per-ticket start / end stamps of fxenv_step_many
+    if (atoi(tl) > 0) {
+      env->timeline_steps = atoi(tl);
+      const size_t nb = (size_t)env->timeline_steps * c.num_envs * 2 * sizeof(long long);
+      cudaMalloc(&env->P.timeline, nb);
+      cudaMemset(env->P.timeline, 0, nb);
+    }
+  }
   ce = fx_configure_kernels(env->P);
   if (const char* rb = getenv("FXENV_ROLLOUT_BLOCKS"))  // timing experiments only: grid of the persistent launch
     if (atoi(rb) > 0 && atoi(rb) < env->P.resident_blocks) env->P.resident_blocks = atoi(rb);
@@ -190,10 +197,11 @@ int fxenv_create(const FxConfig* cfg, FxEnv** out) {
   const size_t ring = (c.reward == FX_REWARD_SHARPE) ? (size_t)c.sharpe_window : 1;
   SlabPlan plan;
   const size_t capP = (size_t)cap + FXO_SLACK;
-  size_t o_d[9], o_start, o_i[11], o_flags, o_ring, o_welford, o_meta, o_p0, o_p1, o_sz, o_nbar;
+  size_t o_d[9], o_start, o_i[11], o_flags, o_ring, o_welford, o_meta, o_p0, o_p1, o_sz, o_nbar, o_rstats;
   for (int i = 0; i < 9; i++) o_d[i] = plan.add(N * 8);
   o_start = plan.add(N * 8);
   o_nbar = plan.add(N * 6 * 8);
+  o_rstats = plan.add(N * FX_RS_N * 8);
   for (int i = 0; i < 11; i++) o_i[i] = plan.add(N * 4);
   o_flags = plan.add(N * 4);
   o_ring = plan.add(N * ring * 8);
@@ -216,6 +224,7 @@ int fxenv_create(const FxConfig* cfg, FxEnv** out) {
   for (int i = 0; i < 9; i++) *dcols[i] = reinterpret_cast<double*>(b + o_d[i]);
   st.start = reinterpret_cast<int64_t*>(b + o_start);
   st.nbar = reinterpret_cast<double*>(b + o_nbar);
+  st.rstats = reinterpret_cast<double*>(b + o_rstats);
   int32_t** icols[11] = {&st.t, &st.total_bars, &st.position, &st.bar_index, &st.trades, &st.n_orders,
                          &st.sh_len, &st.sh_head, &st.sh_last_step, &st.dd_last_step, &st.n_acc};
   for (int i = 0; i < 11; i++) *icols[i] = reinterpret_cast<int32_t*>(b + o_i[i]);
@@ -240,6 +249,7 @@ int fxenv_destroy(FxEnv* env) {
   cudaFree(env->slab);
   cudaFree(env->P.seq);
   cudaFree(env->P.timing);
+  cudaFree(env->P.timeline);
   cudaFree(env->h_actions); cudaFree(env->h_obs); cudaFree(env->h_reward); cudaFree(env->h_term);
   if (env->hstream) cudaStreamDestroy(env->hstream);
   if (env->hcopy) cudaStreamDestroy(env->hcopy);
@@ -372,6 +382,7 @@ int fxenv_step_many(FxEnv* env, int n_steps, const void* actions_dev, float* obs
     if (stream != nullptr) cudaStreamIsCapturing(stream, &rcs);
     if (rcs != cudaStreamCaptureStatusNone) env->seq_tracked = false;
     const bool tracked = env->seq_tracked;
+    if (env->P.timeline && n_steps > env->timeline_steps) return fail(env, FXENV_E_INVALID, "FXENV_TIMELINE smaller than n_steps");
     FX_CUDA(env, fx_launch_rollout(env->P, actions_dev, obs_dev, obs_slots, reward_dev, terminated_dev, n_steps,
                                    tracked ? env->seq_base : 0u, tracked ? env->ticket_base : 0u, !tracked, stream));
     if (tracked) {
@@ -462,6 +473,7 @@ int fxenv_get_info(FxEnv* env, FxInfoPtrs* out) {
   out->position_size = st.psize; out->position_price = st.pprice; out->commission_paid = st.commission_paid;
   out->position = st.position; out->bar_index = st.bar_index; out->total_bars = st.total_bars;
   out->trades = st.trades; out->n_orders = st.n_orders; out->flags = st.flags;
+  out->run_stats = st.rstats;
   return FXENV_OK;
 }
 
@@ -488,6 +500,16 @@ int fxenv_set_state(FxEnv* env, const void* buf_host, int64_t nbytes) {
 }
 
 int64_t fxenv_launch_count(const FxEnv* env) { return env ? env->launches : -1; }
+
+/* debug (FXENV_TIMELINE=K, timing build): copies the [K][num_envs][2] ticket start / end stamps; returns K or <0 */
+int fxenv_debug_timeline(FxEnv* env, long long* out_host) {
+  if (!env || !out_host || !env->P.timeline) return FXENV_E_STATE;
+  DeviceGuard g(env->device);
+  cudaDeviceSynchronize();
+  if (cudaMemcpy(out_host, env->P.timeline, (size_t)env->timeline_steps * env->P.cfg.num_envs * 2 * sizeof(long long),
+                 cudaMemcpyDeviceToHost) != cudaSuccess) return FXENV_E_CUDA;
+  return env->timeline_steps;
+}
 
 /* debug (FXENV_TIMING=1): copies the [num_envs][FX_NSTAMP] phase stamps of the last step; returns FX_NSTAMP or <0 */
 int fxenv_debug_timings(FxEnv* env, long long* out_host) {

@@ -126,8 +126,92 @@ FX_HD void fx_pseudo_execute(const FxConfig& c, double size, double price, doubl
   }
 }
 
+// ---- end-of-run statistics: what backtrader's DrawDown / TradeAnalyzer / SQN analyzers (attached by
+// app/bt_bridge.py:230-234) hold when the run ends; GymFxEnv.summary() -> metrics_plugins/default_metrics.py:48-60 reads
+// max.drawdown, max.moneydown, total.total, won.total, lost.total, pnl.net.average and sqn from them.  One record of
+// FX_RS_N doubles per env (the counters are stored as doubles: exact far beyond any run length).
+enum {
+  FX_RS_DD_MAXVALUE = 0,  // DrawDown._maxvalue: running peak of the broker value
+  FX_RS_DD_MAX_MONEY,     // max.moneydown
+  FX_RS_DD_MAX_PCT,       // max.drawdown (percent)
+  FX_RS_TR_PNL,           // open Trade: gross pnl so far
+  FX_RS_TR_COMM,          // open Trade: commission so far
+  FX_RS_TR_PRICE,         // open Trade: average price (Trade.update's own recurrence, not Position's)
+  FX_RS_PNL_NET,          // TradeAnalyzer pnl.net.total = sum of pnlcomm over closed trades
+  FX_RS_SQN_MEAN,         // running mean / M2 (Welford) of pnlcomm over closed trades -> SQN
+  FX_RS_SQN_M2,
+  FX_RS_OPENED,           // TradeAnalyzer total.total (trades opened)
+  FX_RS_WON,              // won.total  (pnlcomm >= 0)
+  FX_RS_LOST,             // lost.total
+  FX_RS_N
+};
+
+// Accessor the execution code is written against: the device keeps field i in lane i of one register (a single
+// coalesced load / store of the record per env-step), the host build and the reset path use a plain array.
+struct FxRunStatsMem {
+  double* v;
+  FX_HD double get(int i) const { return v[i]; }
+  FX_HD void set(int i, double x) const { v[i] = x; }
+};
+
+struct FxRunStatsNone {  // statistics not tracked by this caller
+  FX_HD double get(int) const { return 0.0; }
+  FX_HD void set(int, double) const {}
+};
+
+template <class RS> struct FxRsOn { static const bool value = true; };
+template <> struct FxRsOn<FxRunStatsNone> { static const bool value = false; };
+
+// DrawDown analyzer, one bar: notify_fund(value) then next()  [backtrader analyzers/drawdown.py, restated]
+template <class RS>
+FX_HD void fx_rs_drawdown(const RS& rs, double value) {
+  double maxv = rs.get(FX_RS_DD_MAXVALUE);
+  if (value > maxv) { maxv = value; rs.set(FX_RS_DD_MAXVALUE, maxv); }
+  const double md = maxv - value;
+  if (md > rs.get(FX_RS_DD_MAX_MONEY)) rs.set(FX_RS_DD_MAX_MONEY, md);
+  // max.drawdown = max(max.drawdown, 100 * md / maxvalue): the division only when it can matter
+  const double mp = rs.get(FX_RS_DD_MAX_PCT);
+  if (100.0 * md > mp * maxv * 0.999999) {
+    const double pct = 100.0 * md / maxv;
+    if (pct > mp) rs.set(FX_RS_DD_MAX_PCT, pct);
+  }
+}
+
+// Strategy._addnotification -> Trade.update for the two bits of one execution (closing part first, then the opening
+// part), and the analyzers' notify_trade when the trade closes / opens  [backtrader strategy.py, trade.py,
+// analyzers/tradeanalyzer.py, analyzers/sqn.py, restated].  `oldsize` = position size before the execution.
+template <class RS>
+FX_HD void fx_rs_trade(const RS& rs, double oldsize, double closed, double opened, double price, double closedcomm,
+                       double openedcomm, int32_t closed_trades_after) {
+  double tprice = rs.get(FX_RS_TR_PRICE), tpnl = rs.get(FX_RS_TR_PNL), tcomm = rs.get(FX_RS_TR_COMM);
+  if (closed != 0.0) {
+    tcomm += closedcomm;
+    tpnl += (-closed) * (price - tprice);  // comminfo.profitandloss(-size, trade.price, price)
+    if (oldsize + closed == 0.0) {         // trade.isclosed
+      const double pnlcomm = tpnl - tcomm;
+      if (pnlcomm >= 0.0) rs.set(FX_RS_WON, rs.get(FX_RS_WON) + 1.0);
+      else rs.set(FX_RS_LOST, rs.get(FX_RS_LOST) + 1.0);
+      rs.set(FX_RS_PNL_NET, rs.get(FX_RS_PNL_NET) + pnlcomm);
+      double mean = rs.get(FX_RS_SQN_MEAN), m2 = rs.get(FX_RS_SQN_M2);
+      const double d = pnlcomm - mean;
+      mean += d / (double)closed_trades_after;
+      m2 += d * (pnlcomm - mean);
+      rs.set(FX_RS_SQN_MEAN, mean); rs.set(FX_RS_SQN_M2, m2);
+      tpnl = 0.0; tcomm = 0.0; tprice = 0.0;  // the next opening bit starts a fresh Trade()
+    }
+  }
+  if (opened != 0.0) {
+    const double tsize = oldsize + closed;
+    tcomm += openedcomm;
+    tprice = (tsize * tprice + opened * price) / (tsize + opened);
+    if (tsize == 0.0) rs.set(FX_RS_OPENED, rs.get(FX_RS_OPENED) + 1.0);  // trade.justopened
+  }
+  rs.set(FX_RS_TR_PRICE, tprice); rs.set(FX_RS_TR_PNL, tpnl); rs.set(FX_RS_TR_COMM, tcomm);
+}
+
 // ---- BackBroker._execute, real form.  Returns true if the order ended in Margin (=> cancel its bracket group) --
-FX_HD bool fx_execute(const FxConfig& c, FxEnvRegs& e, double size, double price) {
+template <class RS>
+FX_HD bool fx_execute(const FxConfig& c, FxEnvRegs& e, double size, double price, const RS& rs) {
   const double pprice_orig = e.pprice, oldsize = e.psize;
   double ps = e.psize, pp = e.pprice, opened, closed;
   fx_pos_update(ps, pp, size, price, opened, closed);  // pseudoupdate on a clone
@@ -163,6 +247,7 @@ FX_HD bool fx_execute(const FxConfig& c, FxEnvRegs& e, double size, double price
     // Trade bookkeeping (strategy._addnotification): a trade closes when the closing part of the execution
     // brings the position to exactly 0 -> BTBridgeStrategy.notify_trade (app/bt_bridge.py:115-117)
     if (closed != 0.0 && oldsize + closed == 0.0) e.trades += 1;
+    if (FxRsOn<RS>::value) fx_rs_trade(rs, oldsize, closed, opened, price, closedcomm, openedcomm, e.trades);
     // BTBridgeStrategy.notify_order counts commission of COMPLETED orders only (app/bt_bridge.py:109-113)
     if (size - execsize == 0.0) {
       double ocomm = 0.0;
@@ -296,7 +381,8 @@ FX_HD double fx_submit_cash_bound(const FxConfig& c, uint32_t meta, double p0, d
 }
 
 // ---- BackBroker.next, step 2: execute entry k (known to hit) in FIFO position ------------------------------------
-FX_HD void fx_exec_entry(const FxConfig& c, FxEnvRegs& e, FxOrderTab& t, int k, const FxBar& b) {
+template <class RS>
+FX_HD void fx_exec_entry(const FxConfig& c, FxEnvRegs& e, FxOrderTab& t, int k, const FxBar& b, const RS& rs) {
   const uint32_t m = t.meta[k];
   if (m & (FXO_DEAD | FXO_SUBMITTED)) return;
   const uint32_t kind = m & FXO_KIND_MASK;
@@ -310,7 +396,7 @@ FX_HD void fx_exec_entry(const FxConfig& c, FxEnvRegs& e, FxOrderTab& t, int k, 
   if (!go) return;
   // Completed or Margin: either way the entry leaves the table.  A child that completes cancels its sibling, a child
   // or parent that goes Margin cancels its whole group -- for a PAIR both mean "the pair is gone".
-  const bool margin = fx_execute(c, e, t.sz[k], px);
+  const bool margin = fx_execute(c, e, t.sz[k], px, rs);
   fx_kill(t, k);
   if (kind == FXO_PARENT) {
     if (margin) fx_kill(t, k + 1);

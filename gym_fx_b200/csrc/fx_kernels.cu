@@ -29,7 +29,7 @@
 
 #define FX_FULL 0xffffffffu
 #ifndef FX_EMIT_EARLY
-#define FX_EMIT_EARLY 1  // emit the observation windows right after the order sweep (see FX_EMIT_OBSERVATION)
+#define FX_EMIT_EARLY 0  // 1: emit the observation windows right after the order sweep (measured: 12.44 vs 12.05 us/step, worse)
 #endif
 
 namespace {
@@ -431,6 +431,16 @@ __device__ __forceinline__ double fx_sharpe_eval_warp(const double* ring, int W,
   return (mean / sd) * sqrt(ann);
 }
 
+// End-of-run statistics record of the env (fx_core.cuh FX_RS_*): field i lives in lane i of ONE register -- a single
+// coalesced load with the state, a single coalesced store if anything changed.  get() broadcasts by shuffle, so the
+// callers (uniform scalar code) must be convergent; set() keeps the value in the owning lane.
+struct FxRunStatsWarp {
+  double& v;
+  int lane;
+  __device__ __forceinline__ double get(int i) const { return __shfl_sync(FX_FULL, v, i); }
+  __device__ __forceinline__ void set(int i, double x) const { if (lane == i) v = x; }
+};
+
 // ---- the fused step --------------------------------------------------------------------------------------------
 #define FX_OP_KILL 1u
 #define FX_OP_ACTIVATE 2u
@@ -503,6 +513,8 @@ __device__ __forceinline__ void fx_step_env(const FxKernelParams& P, const void*
   double* __restrict__ gsz = st.o_sz + obase;
   uint32_t pm0 = gmeta[lane];
   double pp0 = gp0[lane], pp1 = gp1[lane], psz = gsz[lane];
+  double rsv = (lane < FX_RS_N) ? st.rstats[(int64_t)env * FX_RS_N + lane] : 0.0;  // DrawDown / TradeAnalyzer / SQN state
+  const FxRunStatsWarp rs{rsv, lane};
 
 #ifdef FXENV_ENABLE_TIMING
   if (tstamp) {  // keep two consecutive steps: slot = parity of the (pre-step) cursor
@@ -525,6 +537,7 @@ __device__ __forceinline__ void fx_step_env(const FxKernelParams& P, const void*
         st.welford[wi + 1] = 0.0;
       }
       if (lane < 5) st.nbar[(int64_t)env * 6 + lane] = tb.candles[start * (int64_t)C + (lane < 4 ? lane : c.price_col)];
+      if (lane < FX_RS_N) st.rstats[(int64_t)env * FX_RS_N + lane] = (lane == FX_RS_DD_MAXVALUE) ? c.initial_cash : 0.0;
       if (lane == 0) {
         fx_store_all(st, env, e);
         st.t[env] = 0; st.total_bars[env] = total_bars; st.n_orders[env] = 0; st.n_acc[env] = 0; st.sub_need[env] = 0.0;
@@ -586,9 +599,8 @@ __device__ __forceinline__ void fx_step_env(const FxKernelParams& P, const void*
   FX_STAMP_DEP(1, __double_as_longlong(b.o) + __double_as_longlong(b.c));  // the new bar has arrived
 
   // ---- observation windows (app/env.py:160 -> preprocessor.make_observation) from the staged copy.  They depend on
-  // the bar cursor only (not on what the broker / strategy did), so they are emitted right after the order sweep
-  // (FX_EMIT_EARLY): the row's streaming stores then drain while the strategy / reward / write-back run, and the release
-  // fence that publishes the env-step to the next warp (fx_rollout_kernel) finds nothing left to wait for.
+  // the bar cursor only (not on what the broker / strategy did); emitting them right after the order sweep
+  // (FX_EMIT_EARLY, so that the row's stores drain under the strategy / reward / write-back) was measured and is slower.
   // Running z-score statistics while the history window is still growing (or expanding_zscore): warm-up path, one
   // extra round trip here instead of registers held across the broker pass.
 #define FX_EMIT_OBSERVATION()                                                                              \
@@ -670,7 +682,7 @@ __device__ __forceinline__ void fx_step_env(const FxKernelParams& P, const void*
             const uint32_t kind = bm & FXO_KIND_MASK;
             if (kind == FXO_PAIR && !(bm & FXO_ACTIVE)) continue;
             // Completed or Margin: either way the entry leaves the table (a PAIR: sibling / group cancelled)
-            const bool margin = fx_execute(c, e, __shfl_sync(FX_FULL, sz, l), __shfl_sync(FX_FULL, px_lane, l));
+            const bool margin = fx_execute(c, e, __shfl_sync(FX_FULL, sz, l), __shfl_sync(FX_FULL, px_lane, l), rs);
             any_fill = true;
 #ifdef FXENV_ENABLE_TIMING
             n_fills++;
@@ -697,6 +709,12 @@ __device__ __forceinline__ void fx_step_env(const FxKernelParams& P, const void*
 #endif
       }
       fx_mark_to_market(c, e, b.c);
+      // DrawDown analyzer: one notify_fund + next per bar.  With no position and no execution the value is the one of
+      // the previous bar and nothing can change.
+      if (any_fill || e.psize != 0.0) {
+        fx_rs_drawdown(rs, e.value);
+        if (lane < FX_RS_N) st.rstats[(int64_t)env * FX_RS_N + lane] = rsv;
+      }
     }
     FX_STAMP(5);  // broker pass done, marked to market
     // candle of the next call (lanes 0..4): requested now, stored at the end of the env-step
@@ -890,10 +908,6 @@ fx_rollout_kernel(const __grid_constant__ FxKernelParams P, const char* __restri
   const unsigned total = N * (unsigned)n_steps;  // < 2^31 (checked by the caller)
   unsigned* ticket = reinterpret_cast<unsigned*>(P.seq + N);
   asm volatile("griddepcontrol.wait;" ::: "memory");  // everything below touches memory the previous launch wrote
-  // All warps of the grid start at the same instant and would walk through the phases of their first env-steps in
-  // lockstep (every warp loading, then every warp sweeping, then every warp storing its row).  Spreading the start of the
-  // warps that share an SM over about one env-step de-phases them from the first step on.
-  if (P.stagger_ns > 0) __nanosleep((blockIdx.x / (unsigned)P.num_sms) * (unsigned)P.stagger_ns);
   // seq[] and the ticket counter are never reset: this launch's values start at seq_base / ticket_base (kept by the
   // host: every launch leaves seq[env] = seq_base + n_steps and the counter at ticket_base + total + #warps, because
   // each warp draws exactly one ticket >= total).  Unsigned differences make the 2^32 wrap harmless.
@@ -910,10 +924,16 @@ fx_rollout_kernel(const __grid_constant__ FxKernelParams P, const char* __restri
       if (lane == 0) { while ((unsigned)fx_ld_acquire(P.seq + env) != seq_base + k) __nanosleep(32); }
       __syncwarp();
     }
+#ifdef FXENV_ENABLE_TIMING
+    if (P.timeline && lane == 0) { long long g__; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g__)); P.timeline[((size_t)k * N + env) * 2] = g__; }
+#endif
     fx_step_env<STRAT, REWARD, FAST5>(P, actions, obs, reward, nullptr, terminated, (int)env, lane, ws, phase, k * N,
                                       (k % (unsigned)obs_slots) * N);
     __syncwarp();
     if (lane == 0) fx_st_release(P.seq + env, (int)(seq_base + k + 1u));
+#ifdef FXENV_ENABLE_TIMING
+    if (P.timeline && lane == 0) { long long g__; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g__)); P.timeline[((size_t)k * N + env) * 2 + 1] = g__; }
+#endif
     g = __shfl_sync(FX_FULL, g_next, 0);
     phase++;
   }
@@ -943,6 +963,7 @@ __global__ void fx_reset_kernel(const __grid_constant__ FxKernelParams P, const 
   st.n_orders[env] = 0;
   st.n_acc[env] = 0;
   st.sub_need[env] = 0.0;
+  for (int j = 0; j < FX_RS_N; j++) st.rstats[(int64_t)env * FX_RS_N + j] = (j == FX_RS_DD_MAXVALUE) ? c.initial_cash : 0.0;
   for (int j = 0; j < 5; j++) st.nbar[(int64_t)env * 6 + j] = tb.candles[start * (int64_t)c.n_cols + (j < 4 ? j : c.price_col)];
   if (fx_uses_running_stats(c)) {
     for (int f = 0; f < c.n_features; f++) {

@@ -32,6 +32,7 @@ struct FxDeviceState {
   int32_t *t, *total_bars, *position, *bar_index, *trades, *n_orders, *n_acc;
   int32_t *sh_len, *sh_head, *sh_last_step, *dd_last_step;
   uint32_t* flags;
+  double* rstats;    // [N][FX_RS_N] end-of-run statistics: DrawDown / TradeAnalyzer / SQN state (fx_core.cuh FX_RS_*)
   double* sh_ring;   // [N][sharpe_window]
   double* welford;   // [N][FXENV_MAX_FEATURES][2] running {mean, M2} of each feature column over rows [0, s)
   uint32_t* o_meta;  // [N][cap + FXO_SLACK]  order table, entry-major per env (a warp scans one env coalesced)
@@ -47,6 +48,7 @@ struct FxKernelParams {
   double inv_initial_cash;  // 1 / (initial_cash or 1.0)
   int32_t* seq;             // [N + 1] per-env sequence words of a fxenv_step_many batch + the ticket counter (fx_rollout_kernel)
   long long* timing;        // debug (FXENV_TIMING=1): [N][FX_NSTAMP] clock64() phase stamps of the last step, else nullptr
+  long long* timeline;      // debug (FXENV_TIMELINE=K, timing build): [K][N][2] globaltimer at start / end of every ticket
   int32_t obs_dim;
   int32_t cap;              // logical order-table capacity (multiple of 32); arrays hold cap + FXO_SLACK
   int32_t debug;            // timing experiments only (env FXENV_DEBUG, bit mask): 1 skip obs windows, 2 skip broker /
@@ -56,7 +58,6 @@ struct FxKernelParams {
   int32_t tame_data;        // 1: every loaded table value is finite and |x| < 1e100 (no NaN can arise in a z-score)
   int32_t fast_features;    // 5: F == n_cols == 5 with identity columns (the [W][5] block is one contiguous span)
   int32_t num_sms;          // SMs of the device (fx_rollout_kernel: CTA b is the (b / num_sms)-th CTA of its SM)
-  int32_t stagger_ns;       // fx_rollout_kernel: start offset between the warps that share an SM (0 = none)
 };
 
 // warps (= envs) per CTA of the step kernel.  One warp per CTA lets the second wave back-fill SM slots as soon as a

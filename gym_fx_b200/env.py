@@ -82,6 +82,7 @@ class GymFxEnv(spaces.EnvBase):
         self._vec: Optional[VecFxEnv] = None
         self._started = False
         self._terminated = False
+        self._closed_analyzers = None
         self._last_equity = self.initial_cash   # bridge.equity survives close() in the reference (app/env.py:258-262)
         self._np_random = np.random.default_rng()
 
@@ -124,6 +125,8 @@ class GymFxEnv(spaces.EnvBase):
 
     def close(self):
         if self._vec is not None:
+            if self._started:
+                self._closed_analyzers = self._vec.analyzers(0)  # run over: the analyzers become visible (see summary())
             self._vec.close()
             self._vec = None
         self._started = False
@@ -153,6 +156,14 @@ class GymFxEnv(spaces.EnvBase):
                 "commission_paid": float(i["commission_paid"][0]), "_pnl": eq - prev}
 
     def summary(self) -> Dict[str, Any]:
+        """app/env.py:256-271.  The reference sees its analyzers only once cerebro.run() has returned -- i.e. after the
+        episode terminated (data exhausted / broke) or after close() -- and an empty dict before;
+        the same rule is kept here, with the analyzer results coming from the step kernel's per-env statistics."""
         final = float(self._vec.info()["equity"][0]) if self._vec is not None else self._last_equity
-        return self.metrics_plugin.summarize(initial_cash=self.initial_cash, final_equity=final, analyzers={},
+        analyzers: Dict[str, Any] = {}
+        if self._vec is not None and self._terminated:
+            analyzers = self._vec.analyzers(0)
+        elif self._vec is None and self._closed_analyzers is not None:
+            analyzers = self._closed_analyzers
+        return self.metrics_plugin.summarize(initial_cash=self.initial_cash, final_equity=final, analyzers=analyzers,
                                              config=self.config)

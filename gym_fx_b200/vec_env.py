@@ -209,21 +209,65 @@ class VecFxEnv:
         return {k: o[:, off:off + int(np.prod(shape))].reshape((o.shape[0],) + tuple(shape))
                 for k, (off, shape) in self.layout.items()}
 
+    def run_stats(self) -> torch.Tensor:
+        """float64 [N, 12] view of the per-env analyzer state (include/fxenv.h FXENV_RS_*)."""
+        v = self._info_views.get("run_stats")
+        if v is None:
+            v = _tensor_from_ptr(self._info_ptrs.run_stats, self.num_envs * _native.RUN_STATS, torch.float64, self.device)
+            v = v.view(self.num_envs, _native.RUN_STATS)
+            self._info_views["run_stats"] = v
+        return v
+
     def summary(self) -> Dict[str, Any]:
-        """Per-env end-of-run summary (GymFxEnv.summary, app/env.py:256-271 -> default_metrics.summarize :22-60) as device
-        tensors, plus fleet aggregates.  Only the fields the reference can fill on the live path exist (App. B #12):
-        equity-derived ones, the closed-trade counter and the commission paid."""
+        """Per-env end-of-run summary as device tensors, plus fleet aggregates: the fields of GymFxEnv.summary()
+        (app/env.py:256-271 -> metrics_plugins/default_metrics.py:48-60).  The analyzer-derived ones (max drawdown,
+        trades won / lost, average trade pnl, SQN) are tracked inside the step kernel -- what backtrader's DrawDown /
+        TradeAnalyzer / SQN analyzers would report if the run ended now; NaN where the reference reports None.
+        `sharpe_ratio` (SharpeRatio over calendar days) is not tracked and stays None."""
         i = self.info()
+        R = _native.RS
+        rs = self.run_stats()
         ic = float(self.cfg.initial_cash)
         eq = i["equity"]
         ret = eq / ic - 1.0 if ic else torch.zeros_like(eq)
+        closed = i["trades"].double()
+        nan = torch.full_like(closed, float("nan"))
+        avg = torch.where(closed > 0, rs[:, R["pnl_net"]] / closed.clamp(min=1.0), nan)
+        sd = torch.sqrt(rs[:, R["sqn_m2"]] / closed.clamp(min=1.0))
+        sqn = torch.where(closed > 1, torch.where(sd > 0, torch.sqrt(closed) * rs[:, R["sqn_mean"]] / sd, nan),
+                          torch.zeros_like(closed))
         return {
-            "initial_cash": ic, "final_equity": eq, "total_return": ret, "trades_total": i["trades"],
+            "initial_cash": ic, "final_equity": eq, "total_return": ret,
+            "max_drawdown_pct": rs[:, R["dd_max_pct"]], "max_drawdown_money": rs[:, R["dd_max_money"]],
+            "sharpe_ratio": None, "sqn": sqn,
+            "trades_total": rs[:, R["opened"]].to(torch.int64), "trades_won": rs[:, R["won"]].to(torch.int64),
+            "trades_lost": rs[:, R["lost"]].to(torch.int64), "trades_closed": i["trades"], "avg_trade_pnl": avg,
             "commission_paid": i["commission_paid"], "position": i["position"], "bar_index": i["bar_index"],
             "mean_total_return": float(ret.mean()), "min_total_return": float(ret.min()),
-            "max_total_return": float(ret.max()), "mean_trades": float(i["trades"].double().mean()),
+            "max_total_return": float(ret.max()), "mean_trades": float(closed.mean()),
+            "worst_max_drawdown_pct": float(rs[:, R["dd_max_pct"]].max()),
+            "fleet_win_rate": float(rs[:, R["won"]].sum() / closed.sum().clamp(min=1.0)),
             "order_overflow_envs": int((i["flags"] & 16).ne(0).sum()),
         }
+
+    def analyzers(self, env: int = 0) -> Dict[str, Any]:
+        """The analyzer results of ONE env in the shape of backtrader's get_analysis() dicts, as GymFxEnv.summary()
+        hands them to the metrics plugin (app/env.py:258-265): trades / drawdown / sqn / sharpe / time_return."""
+        R = _native.RS
+        rs = self.run_stats()[env].cpu().numpy()
+        closed = int(self.info()["trades"][env])
+        trades: Dict[str, Any] = {"total": {"total": int(rs[R["opened"]]), "open": int(rs[R["opened"]]) - closed,
+                                            "closed": closed}}
+        if closed:
+            trades.update(won={"total": int(rs[R["won"]])}, lost={"total": int(rs[R["lost"]])},
+                          pnl={"net": {"total": float(rs[R["pnl_net"]]), "average": float(rs[R["pnl_net"]]) / closed}})
+        if closed > 1:
+            sd = float(np.sqrt(rs[R["sqn_m2"]] / closed))
+            sqn = float(np.sqrt(closed) * rs[R["sqn_mean"]] / sd) if sd > 0 else None
+        else:
+            sqn = 0
+        return {"trades": trades, "sqn": {"sqn": sqn, "trades": closed}, "sharpe": {}, "time_return": {},
+                "drawdown": {"max": {"drawdown": float(rs[R["dd_max_pct"]]), "moneydown": float(rs[R["dd_max_money"]])}}}
 
     def launch_count(self) -> int:
         return int(self.L.fxenv_launch_count(self._h))

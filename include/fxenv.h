@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define FXENV_ABI_VERSION 1
+#define FXENV_ABI_VERSION 2
 #define FXENV_MAX_PAIRS 8
 #define FXENV_MAX_FEATURES 16
 #define FXENV_MAX_COLS 16
@@ -145,7 +145,23 @@ typedef struct FxInfoPtrs {
   const int32_t* trades;
   const int32_t* n_orders;          /* live order-table entries */
   const uint32_t* flags;            /* FX_FLAG_* */
+  /* [num_envs][FXENV_RUN_STATS] float64: what backtrader's DrawDown / TradeAnalyzer / SQN analyzers (attached by
+   * app/bt_bridge.py:230-234) hold for the current episode -- the inputs of GymFxEnv.summary()
+   * (app/env.py:256-271 -> metrics_plugins/default_metrics.py:48-60).  Field order: FXENV_RS_*. */
+  const double* run_stats;
 } FxInfoPtrs;
+
+#define FXENV_RUN_STATS 12
+enum {
+  FXENV_RS_DD_MAXVALUE = 0, /* running peak of the broker value */
+  FXENV_RS_DD_MAX_MONEY,    /* drawdown.max.moneydown */
+  FXENV_RS_DD_MAX_PCT,      /* drawdown.max.drawdown (percent) */
+  FXENV_RS_TR_PNL, FXENV_RS_TR_COMM, FXENV_RS_TR_PRICE, /* the open trade */
+  FXENV_RS_PNL_NET,         /* trades.pnl.net.total (average = / closed trades = FxInfoPtrs.trades) */
+  FXENV_RS_SQN_MEAN, FXENV_RS_SQN_M2, /* running mean / M2 of the closed trades' net pnl: sqn = sqrt(n) * mean / sqrt(M2 / n) */
+  FXENV_RS_OPENED,          /* trades.total.total */
+  FXENV_RS_WON, FXENV_RS_LOST
+};
 
 int fxenv_abi_version(void);
 

@@ -27,6 +27,8 @@ kernel.
 """
 from __future__ import annotations
 
+import copy
+
 import collections
 import datetime as _dt
 import itertools
@@ -214,20 +216,35 @@ class Position:
 
 
 class Trade:
+    """backtrader trade.py, restated from memory [BT-from-memory]: size, average price, accumulated gross pnl and
+    commission of ONE round trip; pnlcomm = pnl - commission (what TradeAnalyzer / SQN read when it closes)."""
+
     def __init__(self):
         self.size = 0
+        self.price = 0.0
+        self.commission = 0.0
+        self.pnl = 0.0
+        self.pnlcomm = 0.0
         self.isclosed = False
         self.isopen = False
         self.justopened = False
 
-    def update(self, size):
+    def update(self, size, price=0.0, commission=0.0):
         if not size:
             return
+        self.commission += commission
         oldsize = self.size
         self.size += size
         self.justopened = bool(not oldsize and size)
         self.isopen = bool(self.size)
         self.isclosed = bool(oldsize and not self.size)
+        if abs(self.size) > abs(oldsize):   # position increased: new average price, no pnl
+            self.price = (oldsize * self.price + size * price) / self.size
+            pnl = 0.0
+        else:                               # reduced / closed: comminfo.profitandloss(-size, self.price, price), stock-like
+            pnl = (-size) * (price - self.price)
+        self.pnl += pnl
+        self.pnlcomm = self.pnl - self.commission
 
 
 class CommInfoBase:
@@ -608,7 +625,7 @@ class BackBroker:
         if execsize:
             position.update(execsize, price)
             order.execute(execsize, price, closed, closedcomm, opened, openedcomm, pnl)
-            order._exbit = (closed, opened)
+            order._exbit = (closed, opened, price, closedcomm, openedcomm)
             self.notify(order)
         if popened and not opened:
             order.margin()
@@ -699,23 +716,118 @@ feeds = _Feeds()
 
 
 # ----------------------------------------------------------------------------
-# Analyzers: attached unconditionally by app/bt_bridge.py:230-234; their results are
-# unreachable on the step path (env.summary() sees them only after cerebro.run
-# returns), so no-op stand-ins are behaviour-preserving for everything we compare.
+# Analyzers: attached unconditionally by app/bt_bridge.py:230-234.  Their results are unreachable on the step path
+# (env.summary() sees them only after cerebro.run returned), so they change nothing that the
+# trajectory goldens compare; DrawDown / TradeAnalyzer / SQN are restated here [BT-from-memory: analyzers/drawdown.py,
+# tradeanalyzer.py, sqn.py] so that the end-of-run summary (metrics_plugins/default_metrics.py:48-60) has an oracle.
+# SharpeRatio(timeframe=Days) / TimeReturn need calendar-day buckets of the equity curve and stay empty.
 # ----------------------------------------------------------------------------
+class _AutoDict(dict):
+    def __missing__(self, key):
+        v = self[key] = _AutoDict()
+        return v
+
+
 class Analyzer:
     def __init__(self, **kw):
         self.kw = kw
+
+    def _fund(self, value):     # Strategy._notify -> analyzer._notify_fund, once per bar, before next()
+        pass
+
+    def _next(self):            # Strategy._next_analyzers, once per bar, after strategy.next()
+        pass
+
+    def _trade(self, trade):    # analyzer._notify_trade
+        pass
+
+    def _stop(self):
+        pass
 
     def get_analysis(self):
         return {}
 
 
+class _DrawDown(Analyzer):
+    def __init__(self, **kw):
+        super().__init__(**kw)
+        self._value, self._maxvalue = 0.0, float("-inf")
+        self.rets = {"len": 0, "drawdown": 0.0, "moneydown": 0.0, "max": {"len": 0, "drawdown": 0.0, "moneydown": 0.0}}
+
+    def _fund(self, value):
+        self._value = value
+        self._maxvalue = max(self._maxvalue, value)
+
+    def _next(self):
+        r = self.rets
+        r["moneydown"] = moneydown = self._maxvalue - self._value
+        r["drawdown"] = drawdown = 100.0 * moneydown / self._maxvalue
+        r["max"]["moneydown"] = max(r["max"]["moneydown"], moneydown)
+        r["max"]["drawdown"] = max(r["max"]["drawdown"], drawdown)
+        r["len"] = r["len"] + 1 if drawdown else 0
+        r["max"]["len"] = max(r["max"]["len"], r["len"])
+
+    def get_analysis(self):
+        return self.rets
+
+
+class _TradeAnalyzer(Analyzer):
+    def __init__(self, **kw):
+        super().__init__(**kw)
+        self.rets = _AutoDict()
+        self.rets["total"]["total"] = 0
+
+    def _trade(self, trade):
+        t = self.rets
+        if trade.justopened:
+            t["total"]["total"] += 1
+            t["total"]["open"] = t["total"].get("open", 0) + 1
+        elif trade.isclosed:
+            t["total"]["open"] = t["total"].get("open", 0) - 1
+            t["total"]["closed"] = t["total"].get("closed", 0) + 1
+            won = trade.pnlcomm >= 0.0
+            for key, hit in (("won", won), ("lost", not won)):
+                t[key]["total"] = t[key].get("total", 0) + int(hit)
+            net = t["pnl"]["net"]
+            net["total"] = net.get("total", 0.0) + trade.pnlcomm
+            net["average"] = net["total"] / t["total"]["closed"]
+
+    def get_analysis(self):
+        return self.rets
+
+
+class _SQN(Analyzer):
+    def __init__(self, **kw):
+        super().__init__(**kw)
+        self.pnl, self.rets = [], {}
+
+    def _trade(self, trade):
+        if trade.isclosed:
+            self.pnl.append(trade.pnlcomm)
+
+    def _stop(self):
+        import math
+        n = len(self.pnl)
+        if n > 1:
+            av = math.fsum(self.pnl) / n
+            sd = math.sqrt(math.fsum((x - av) ** 2 for x in self.pnl) / n)
+            try:
+                sqn = math.sqrt(n) * av / sd
+            except ZeroDivisionError:
+                sqn = None
+        else:
+            sqn = 0
+        self.rets = {"sqn": sqn, "trades": n}
+
+    def get_analysis(self):
+        return self.rets
+
+
 class _Analyzers:
-    TradeAnalyzer = type("TradeAnalyzer", (Analyzer,), {})
+    TradeAnalyzer = _TradeAnalyzer
     SharpeRatio = type("SharpeRatio", (Analyzer,), {})
-    DrawDown = type("DrawDown", (Analyzer,), {})
-    SQN = type("SQN", (Analyzer,), {})
+    DrawDown = _DrawDown
+    SQN = _SQN
     TimeReturn = type("TimeReturn", (Analyzer,), {})
 
 
@@ -723,7 +835,8 @@ analyzers = _Analyzers()
 
 
 class _AnalyzerBag:
-    pass
+    def _all(self):
+        return [a for a in vars(self).values() if isinstance(a, Analyzer)]
 
 
 # ----------------------------------------------------------------------------
@@ -826,18 +939,23 @@ class Strategy:
         exbit = getattr(order, "_exbit", None)
         if exbit is None:
             return
-        closed, opened = exbit
+        closed, opened = exbit[0], exbit[1]
+        price = exbit[2] if len(exbit) > 2 else 0.0
+        closedcomm = exbit[3] if len(exbit) > 3 else 0.0
+        openedcomm = exbit[4] if len(exbit) > 4 else 0.0
         if self._trade is None:
             self._trade = Trade()
         trade = self._trade
         if closed:
-            trade.update(closed)
+            trade.update(closed, price, closedcomm)
             if trade.isclosed:
-                self._tradespending.append(trade)
+                self._tradespending.append(copy.copy(trade))
         if opened:
             if trade.isclosed:
                 trade = self._trade = Trade()
-            trade.update(opened)
+            trade.update(opened, price, openedcomm)
+            if trade.justopened:
+                self._tradespending.append(copy.copy(trade))
 
     def _notify(self):
         pending, self._orderspending = self._orderspending, []
@@ -845,7 +963,12 @@ class Strategy:
             self.notify_order(order)
         tpending, self._tradespending = self._tradespending, []
         for trade in tpending:
+            for an in self.analyzers._all():
+                an._trade(trade)
             self.notify_trade(trade)
+        value = self.broker.getvalue()
+        for an in self.analyzers._all():
+            an._fund(value)
 
 
 class Cerebro:
@@ -912,6 +1035,8 @@ class Cerebro:
                     s.nextstart()
                 else:
                     s.next()
+                for an in s.analyzers._all():   # Strategy._next -> _next_analyzers, after next()
+                    an._next()
             first = False
             if self._event_stop:
                 break
@@ -919,4 +1044,6 @@ class Cerebro:
             data._idx = data._n - 1
         for s in strats:
             s.stop()
+            for an in s.analyzers._all():
+                an._stop()
         return strats

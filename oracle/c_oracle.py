@@ -53,6 +53,7 @@ def lib():
         L.fxo_observe.argtypes = [C.c_void_p, C.c_void_p]
         L.fxo_info.argtypes = [C.c_void_p, C.POINTER(FxoInfo)]
         L.fxo_max_live_orders.argtypes = [C.c_void_p]
+        L.fxo_summary.argtypes = [C.c_void_p, C.c_void_p]
         L.fxo_obs_dim.restype = C.c_int64
         L.fxo_obs_dim.argtypes = [C.POINTER(FxConfig)]
         L.fxo_step_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
@@ -143,6 +144,16 @@ class OracleVec:
         dt = {"position": np.int32, "bar_index": np.int32, "total_bars": np.int32, "trades": np.int32,
               "n_orders": np.int32, "flags": np.uint32}
         return {k: np.asarray(v, dt.get(k, np.float64)) for k, v in out.items()}
+
+    SUMMARY_FIELDS = ("max_drawdown_pct", "max_drawdown_money", "trades_total", "trades_won", "trades_lost",
+                      "avg_trade_pnl", "sqn", "trades_closed")
+
+    def summary(self):
+        """Analyzer-derived fields of metrics_plugins/default_metrics.py:48-60, one array per field (NaN = None)."""
+        out = np.zeros((self.N, len(self.SUMMARY_FIELDS)))
+        for i, h in enumerate(self.envs):
+            self.L.fxo_summary(h, out[i].ctypes.data)
+        return {k: out[:, j].copy() for j, k in enumerate(self.SUMMARY_FIELDS)}
 
     def max_live_orders(self):
         return max(self.L.fxo_max_live_orders(h) for h in self.envs)

@@ -129,6 +129,9 @@ def run_reference(
                 break
     total_bars = env.total_bars
     env.close()
+    # After close() the worker thread has returned from cerebro.run(), so summary() now sees the analyzers
+    # (app/env.py:256-271; before close() they are empty): the end-of-run metrics oracle.
+    summary = env.summary()
     out = {
         "obs": np.stack(rec["obs"]).astype(np.float32),
         "reward": np.asarray(rec["reward"], np.float64),
@@ -140,5 +143,6 @@ def run_reference(
         "trades": np.asarray(rec["trades"], np.int32),
         "commission_paid": np.asarray(rec["commission_paid"], np.float64),
         "total_bars": np.asarray([total_bars], np.int64),
+        "summary": summary,
     }
     return out

@@ -79,3 +79,27 @@ def assert_traj_matches(traj, g, *, obs_rtol=1e-6, obs_atol=1e-6, reward_rtol=1e
     rows = g["obs_rows"]
     np.testing.assert_allclose(np.asarray(traj["obs"])[rows], g["obs"], rtol=obs_rtol, atol=obs_atol,
                                err_msg=f"{label}: obs")
+
+
+SUMMARY_KEYS = ("max_drawdown_pct", "max_drawdown_money", "trades_total", "trades_won", "trades_lost", "avg_trade_pnl", "sqn")
+
+
+def assert_summary_matches(got, want, label="", sqn_rtol=1e-9):
+    """got / want: dicts with the analyzer-derived fields of metrics_plugins/default_metrics.py:48-60 (None or NaN = the
+    reference's None).  Counters and the drawdown / average-pnl values (same fp64 operations in the same order) must be
+    equal; `sqn` is a running-moment evaluation on the device side vs math.fsum in the reference: 1e-9 relative."""
+    def norm(v):
+        if v is None:
+            return None
+        v = float(v)
+        return None if v != v else v
+    for k in SUMMARY_KEYS:
+        a, b = norm(got[k]), norm(want[k])
+        if k.startswith("trades_"):
+            assert int(a or 0) == int(b or 0), f"{label}: {k} {a} != {b}"
+        elif k == "sqn":
+            assert (a is None) == (b is None), f"{label}: sqn {a} vs {b}"
+            if a is not None:
+                assert abs(a - b) <= sqn_rtol * max(1.0, abs(b)), f"{label}: sqn {a!r} vs {b!r}"
+        else:
+            assert a == b, f"{label}: {k} {a!r} != {b!r}"

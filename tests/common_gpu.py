@@ -56,3 +56,27 @@ def compare_info(tag, gi, oi):
         a, b = gi[k], oi[k]
         bad = np.nonzero(a != b)[0]
         assert bad.size == 0, f"{tag}: {k} not bit-exact at env {bad[0]}: {a[bad[0]]!r} vs {b[bad[0]]!r}"
+
+
+def gpu_summary(env, i=None):
+    """VecFxEnv.summary() as numpy: dict of per-env arrays (or of env i's scalars) of the analyzer-derived fields."""
+    sm = env.summary()
+    out = {k: sm[k].cpu().numpy() for k in ("max_drawdown_pct", "max_drawdown_money", "trades_total", "trades_won",
+                                            "trades_lost", "trades_closed", "avg_trade_pnl", "sqn")}
+    return out if i is None else {k: v[i] for k, v in out.items()}
+
+
+def compare_summary(tag, gs, osum):
+    """GPU summary arrays vs OracleVec.summary(): drawdown / average pnl bit-exact, counters equal, sqn 1e-9."""
+    for k in ("trades_total", "trades_won", "trades_lost", "trades_closed"):
+        np.testing.assert_array_equal(gs[k].astype(np.int64), osum[k].astype(np.int64), err_msg=f"{tag}: {k}")
+    for k in ("max_drawdown_pct", "max_drawdown_money", "avg_trade_pnl"):
+        a, b = gs[k], osum[k]
+        assert np.array_equal(np.isnan(a), np.isnan(b)), f"{tag}: {k} NaN pattern"
+        ok = ~np.isnan(a)
+        bad = np.nonzero(a[ok] != b[ok])[0]
+        assert bad.size == 0, f"{tag}: {k} not bit-exact at env {bad[0]}: {a[ok][bad[0]]!r} vs {b[ok][bad[0]]!r}"
+    a, b = gs["sqn"], osum["sqn"]
+    assert np.array_equal(np.isnan(a), np.isnan(b)), f"{tag}: sqn NaN pattern"
+    ok = ~np.isnan(a)
+    np.testing.assert_allclose(a[ok], b[ok], rtol=1e-9, atol=1e-12, err_msg=f"{tag}: sqn")

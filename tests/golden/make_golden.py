@@ -74,6 +74,7 @@ def generate(sc, outdir):
         keep = np.unique(np.concatenate([np.arange(0, min(n, 40)), np.arange(0, n, every), [n - 1]]))
     else:
         keep = np.arange(n)
+    summary = traj.pop("summary")   # GymFxEnv.summary() after close(): includes the analyzers' results
     out = {k: v for k, v in traj.items() if k != "obs"}
     out["obs"] = traj["obs"][keep]
     out["obs_rows"] = keep.astype(np.int64)
@@ -82,6 +83,7 @@ def generate(sc, outdir):
     out["actions"] = actions
     meta = dict(name=sc["name"], columns=columns, config=cfg, plugins=sc["plugins"],
                 children_same_bar=bool(sc.get("children_same_bar", False)),
+                summary=summary,
                 reference="harveybc/gym-fx@ad8bbc41 over oracle/bt_shim", python=sys.version.split()[0],
                 numpy=np.__version__)
     out["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)

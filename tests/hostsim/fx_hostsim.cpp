@@ -18,6 +18,7 @@ struct HsEnv {
   int32_t t, total_bars; int64_t start;
   std::vector<uint32_t> meta; std::vector<double> p0, p1, sz; int n;
   std::vector<double> ring; int32_t sh_len, sh_head, sh_last, dd_last; double dd_peak;
+  double rs[FX_RS_N];  // end-of-run statistics (DrawDown / TradeAnalyzer / SQN state)
 };
 
 extern "C" {
@@ -43,6 +44,8 @@ void hs_reset(HsEnv* h, int64_t start) {
   e.cash = c.initial_cash; e.value = c.initial_cash; e.psize = 0; e.pprice = 0; e.equity = e.prev_equity = c.initial_cash;
   e.commission_paid = 0; e.trades = 0; e.position = 0; e.flags = 0;
   e.price = h->tbl[start * c.n_cols + 3]; e.bar_index = 1;
+  for (int i = 0; i < FX_RS_N; i++) h->rs[i] = 0.0;
+  h->rs[FX_RS_DD_MAXVALUE] = c.initial_cash;  // bar 0: notify_fund(cash), next()
 }
 
 void hs_step(HsEnv* h, double action_in, double* reward, uint8_t* term) {
@@ -70,9 +73,9 @@ void hs_step(HsEnv* h, double action_in, double* reward, uint8_t* term) {
       hit[k] = fx_entry_hits(tab.meta[k], tab.p0[k], tab.p1[k], b);
     }
     fx_check_submitted(c, e, tab, first_sub);
-    for (int k = 0; k < n; k++) if (hit[k]) fx_exec_entry(c, e, tab, k, b);
+    for (int k = 0; k < n; k++) if (hit[k]) fx_exec_entry(c, e, tab, k, b, FxRunStatsMem{h->rs});
   }
-  if (advance) fx_mark_to_market(c, e, b.c);
+  if (advance) { fx_mark_to_market(c, e, b.c); fx_rs_drawdown(FxRunStatsMem{h->rs}, e.value); }
   if (!exhausted) {
     double atr = 0; bool ready = false;
     if (c.strategy == FX_STRATEGY_ATR_SLTP && action != 0) {
@@ -126,6 +129,8 @@ void hs_info(HsEnv* h, double* d7, int32_t* i5, uint32_t* flags) {
   i5[0] = e.position; i5[1] = e.bar_index; i5[2] = h->total_bars; i5[3] = e.trades; i5[4] = h->n;
   *flags = e.flags;
 }
+
+void hs_stats(HsEnv* h, double* out) { for (int i = 0; i < FX_RS_N; i++) out[i] = h->rs[i]; }
 
 // Cross-check of the two forms of the trigger test the kernel uses: fx_entry_fill (select form, also returns the
 // execution price; what the CUDA kernel evaluates per lane) against fx_entry_hits + the branchy fx_match_* rules (what

@@ -25,6 +25,7 @@ def lib():
         L.hs_step.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_uint8)]
         L.hs_scalars.argtypes = [C.c_void_p, C.c_void_p]
         L.hs_info.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.hs_stats.argtypes = [C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -64,3 +65,9 @@ class HostSimEnv:
         return dict(equity=d[0], prev_equity=d[1], price=d[2], cash=d[3], position_size=d[4], position_price=d[5],
                     commission_paid=d[6], position=int(i[0]), bar_index=int(i[1]), total_bars=int(i[2]),
                     trades=int(i[3]), n_orders=int(i[4]), flags=int(f[0]))
+
+    def stats(self):
+        """The FX_RS_* record (fx_core.cuh): DrawDown / TradeAnalyzer / SQN state."""
+        out = np.zeros(12)
+        self.L.hs_stats(self.h, out.ctypes.data)
+        return out

@@ -36,7 +36,7 @@ def test_library_exports_every_header_symbol():
     L = _native.load()
     for sym in declared:
         assert hasattr(L, sym), f"libfxenv.so does not export {sym}"
-    assert L.fxenv_abi_version() == 1
+    assert L.fxenv_abi_version() == 2
     assert sorted(_native.EXPORTS) == declared
 
 

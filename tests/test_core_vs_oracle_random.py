@@ -62,3 +62,13 @@ def test_product_core_matches_oracle_on_random_configs(seed):
             assert ci[key] == oi[key][0], (seed, k, key, repr(ci[key]), repr(oi[key][0]))
         if t:
             break
+    # end-of-run statistics of the product core (FX_RS_* record) against the oracle's analyzers
+    rs, osum = core.stats(), {k: v[0] for k, v in orc.summary().items()}
+    closed = core.info()["trades"]
+    assert rs[2] == osum["max_drawdown_pct"] and rs[1] == osum["max_drawdown_money"], (seed, rs[:3], osum)
+    assert (rs[9], rs[10], rs[11], closed) == (osum["trades_total"], osum["trades_won"], osum["trades_lost"], osum["trades_closed"])
+    if closed:
+        assert rs[6] / closed == osum["avg_trade_pnl"], (seed, rs[6] / closed, osum["avg_trade_pnl"])
+    if closed > 1 and osum["sqn"] == osum["sqn"]:
+        sqn = np.sqrt(closed) * rs[7] / np.sqrt(rs[8] / closed)
+        np.testing.assert_allclose(sqn, osum["sqn"], rtol=1e-9, err_msg=f"seed {seed}: sqn")

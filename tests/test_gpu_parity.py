@@ -11,8 +11,8 @@ import pytest
 import torch
 
 import scenarios as S
-from common import assert_traj_matches, config_from_meta, golden_names, load_golden, replay
-from common_gpu import GpuVec, compare_info, compare_step
+from common import assert_summary_matches, assert_traj_matches, config_from_meta, golden_names, load_golden, replay
+from common_gpu import GpuVec, compare_info, compare_step, compare_summary, gpu_summary
 from gym_fx_b200.config import lower_config
 from gym_fx_b200.synth import start_offsets, synth_candles, synth_minutes
 from oracle.c_oracle import OracleVec
@@ -33,8 +33,11 @@ def test_gpu_matches_reference_golden(name):
     env = GpuVec(cfg, [g["candles"]], [g["minutes"]])
     traj = replay(env, g, env.info)
     assert not np.any(env.info()["flags"] & 16), "order table overflow"
+    summ = gpu_summary(env.env, 0)
     env.close()
     assert_traj_matches(traj, g, obs_rtol=1e-5, obs_atol=2e-6, label=name)
+    # the reference's GymFxEnv.summary() after the run (DrawDown / TradeAnalyzer / SQN): section 8f #3
+    assert_summary_matches(summ, g["meta"]["summary"], label=name)
 
 
 def test_gpu_reference_known_answer():
@@ -99,6 +102,7 @@ def test_gpu_matches_oracle_vectorised(case):
         if k % 25 == 0 or k == steps - 1:
             compare_info(f"{case} step {k}", gpu.info(), orc.info())
     assert not np.any(gpu.info()["flags"] & 16), "order table overflow"
+    compare_summary(case, gpu_summary(gpu.env), orc.summary())
     total = steps * N * gpu.env.obs_dim
     assert inexact <= max(10, total * 1e-4), f"{inexact}/{total} obs floats not bit-identical to the oracle"
     gpu.close()
@@ -117,6 +121,8 @@ def test_gpu_episode_end_and_auto_reset():
             a = rng.integers(0, 3, 64).astype(np.int32)
             compare_step(f"auto={auto} step {k}", gpu.step(a), orc.step(a))
             compare_info(f"auto={auto} step {k}", gpu.info(), orc.info())
+            if k % 10 == 0 or k == 94:
+                compare_summary(f"auto={auto} step {k}", gpu_summary(gpu.env), orc.summary())
             if k == 50:
                 mask = (np.arange(64) % 3 == 0).astype(np.uint8)
                 np.testing.assert_allclose(gpu.reset(None, mask), orc.reset(None, mask), rtol=1e-5, atol=2e-6)

@@ -12,7 +12,7 @@ import pytest
 import torch
 
 import scenarios as S
-from common_gpu import GpuVec, compare_info, compare_step
+from common_gpu import GpuVec, compare_info, compare_step, compare_summary, gpu_summary
 from gym_fx_b200.config import lower_config
 from gym_fx_b200.synth import synth_candles, synth_minutes
 from oracle.c_oracle import OracleVec
@@ -57,6 +57,7 @@ def test_cuda_kernel_matches_oracle_on_random_configs(seed):
             compare_info(f"seed {seed} step {k}", gi, orc.info())
             deepest = max(deepest, int(gi["n_orders"].max()))
             assert not np.any(gi["flags"] & 16), f"seed {seed}: order table overflow at step {k}"
+    compare_summary(f"seed {seed}", gpu_summary(gpu.env), orc.summary())
     gpu.close()
     orc.close()
 
@@ -85,6 +86,8 @@ def test_cuda_kernel_deep_order_tables_cross_chunk_carry():
             deepest = max(deepest, int(gi["n_orders"].max()))
             margin_seen |= bool(np.any(gi["cash"] < 1500.0 * 1.2))
     assert deepest > 64, f"only {deepest} live entries: the cross-chunk paths were not exercised"
+    assert margin_seen, "cash never got close to the order size: the margin paths were not exercised"
+    compare_summary("deep", gpu_summary(gpu.env), orc.summary())
     assert not np.any(gpu.info()["flags"] & 16)
     gpu.close()
     orc.close()

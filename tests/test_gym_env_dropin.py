@@ -18,7 +18,7 @@ import os
 import numpy as np
 import pytest
 
-from common import load_golden
+from common import assert_summary_matches, load_golden
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GROUPS = {"data_feed": "data_feed.plugins", "broker": "broker.plugins", "strategy": "strategy.plugins",
@@ -202,8 +202,14 @@ def _replay_golden(name, tmp_path, env_class=None):
         terminated_before = terminated
     summary = env.summary()
     assert summary["final_equity"] == g["equity"][n - 1]
+    if not terminated_before:   # run still going: the reference's analyzers are not visible yet
+        assert summary["max_drawdown_pct"] is None and summary["trades_total"] == 0 and summary["avg_trade_pnl"] is None
     env.close()
-    assert env.summary()["final_equity"] == g["equity"][n - 1]   # bridge.equity survives close() in the reference
+    after = env.summary()        # after close() cerebro.run has returned: analyzers visible, bridge.equity kept
+    assert after["final_equity"] == g["equity"][n - 1]
+    assert_summary_matches(after, meta["summary"], label=name)
+    if terminated_before:
+        assert_summary_matches(summary, meta["summary"], label=name + " (terminated, before close)")
     return summary, g
 
 

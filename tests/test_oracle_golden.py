@@ -5,7 +5,7 @@
 import numpy as np
 import pytest
 
-from common import assert_traj_matches, config_from_meta, golden_names, load_golden, replay
+from common import assert_summary_matches, assert_traj_matches, config_from_meta, golden_names, load_golden, replay
 from oracle.c_oracle import OracleVec
 
 
@@ -14,6 +14,7 @@ def _run(name):
     cfg = config_from_meta(g["meta"])
     env = OracleVec(cfg, [g["candles"]], [g["minutes"]])
     traj = replay(env, g, env.info)
+    traj["summary"] = {k: v[0] for k, v in env.summary().items()}
     return g, traj
 
 
@@ -34,3 +35,11 @@ def test_reference_known_answer_flat():
 def test_oracle_matches_golden(name):
     g, traj = _run(name)
     assert_traj_matches(traj, g, label=name)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_oracle_summary_matches_reference_analyzers(name):
+    """GymFxEnv.summary() of the reference after the run has ended (app/env.py:256-271): the analyzer-derived fields of
+    metrics_plugins/default_metrics.py:48-60 (backtrader DrawDown / TradeAnalyzer / SQN, restated in oracle/bt_shim)."""
+    g, traj = _run(name)
+    assert_summary_matches(traj["summary"], g["meta"]["summary"], label=name, sqn_rtol=1e-12)
