@@ -15,10 +15,21 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, os.environ.get("FXENV_LIB", "libfxenv.so"))  # FXENV_LIB: experiment builds
 CSRC = os.path.join(_HERE, "csrc")
 
+class FxPolicyWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("w1", "b1", "w2", "b2", "w_pi", "b_pi", "w_v", "b_v")]
+
+
+class FxRollout(C.Structure):
+    _fields_ = [("horizon", C.c_int32), ("obs_slots", C.c_int32), ("obs", C.c_void_p), ("actions", C.c_void_p),
+                ("logp", C.c_void_p), ("value", C.c_void_p), ("reward", C.c_void_p), ("done", C.c_void_p),
+                ("gumbel", C.c_void_p), ("seed", C.c_uint64)]
+
+
 EXPORTS = [
     "fxenv_abi_version", "fxenv_create", "fxenv_destroy", "fxenv_last_error", "fxenv_load_candles", "fxenv_obs_dim",
     "fxenv_reset", "fxenv_observe", "fxenv_step", "fxenv_step_many", "fxenv_step_host", "fxenv_get_info",
     "fxenv_state_bytes", "fxenv_get_state", "fxenv_set_state", "fxenv_launch_count", "fxenv_step_many_engine",
+    "fxenv_policy_create", "fxenv_policy_set_weights", "fxenv_policy_destroy", "fxenv_rollout",
 ]
 
 
@@ -93,6 +104,10 @@ def load():
     L.fxenv_launch_count.argtypes = [vp]
     L.fxenv_step_many_engine.restype = C.c_int
     L.fxenv_step_many_engine.argtypes = [vp, C.c_int]
+    L.fxenv_policy_create.argtypes = [vp, C.POINTER(vp)]
+    L.fxenv_policy_set_weights.argtypes = [vp, C.POINTER(FxPolicyWeights), vp]
+    L.fxenv_policy_destroy.argtypes = [vp]
+    L.fxenv_rollout.argtypes = [vp, vp, C.POINTER(FxRollout), vp]
     if L.fxenv_abi_version() != 2:
         raise FxEnvError("libfxenv.so ABI version mismatch")
     _lib = L

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "fx_kernels.cuh"
+#include "fx_policy.cuh"
 
 namespace {
 
@@ -519,6 +520,170 @@ int fxenv_debug_timings(FxEnv* env, long long* out_host) {
   if (cudaMemcpy(out_host, env->P.timing, (size_t)env->P.cfg.num_envs * 2 * FX_NSTAMP * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess)
     return FXENV_E_CUDA;
   return FX_NSTAMP;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------- closed loop (policy)
+struct FxPolicy {
+  FxEnv* env = nullptr;
+  int k_pad = 0;                       // obs_dim padded to a multiple of 64 (bf16 row stride of the observation copy)
+  uint16_t* w1 = nullptr;              // bf16 [256][k_pad]
+  uint16_t* w2 = nullptr;              // bf16 [256][256]
+  float* fparams = nullptr;            // b1[256] | b2[256] | head_w[4][256] | head_b[4]
+  uint16_t* obs16[2] = {nullptr, nullptr};  // bf16 [num_envs][k_pad], double buffered
+  int32_t* scratch_act = nullptr;      // bootstrap evaluation: action / logp are discarded
+  float* scratch_logp = nullptr;
+  CUtensorMap map_obs[2], map_w1, map_w2;
+  FxPolicyDev dev;
+  bool has_weights = false;
+  struct { cudaGraphExec_t exec = nullptr; FxRollout io; } cached;
+};
+
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 2-D bf16 [rows][cols] row-major tensor, box = 64 columns (128 bytes) x box_rows rows, 128-byte swizzle, OOB -> 0
+int make_map(FxEnv* env, CUtensorMap* map, void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  static EncodeTiledFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn)
+      return fail(env, FXENV_E_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+    encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {cols * 2};
+  const cuuint32_t box[2] = {64, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(env, FXENV_E_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+  return FXENV_OK;
+}
+
+cudaError_t enqueue_rollout(FxEnv* env, FxPolicy* pol, const FxRollout& io, cudaStream_t s) {
+  const size_t N = (size_t)env->P.cfg.num_envs, D = (size_t)env->P.obs_dim;
+  const int H = io.horizon, slots = io.obs_slots;
+  cudaError_t e = fx_launch_observe(env->P, io.obs, s, pol->obs16[0], pol->k_pad);  // the current observation, both copies
+  if (e != cudaSuccess) return e;
+  for (int t = 0; t < H; t++) {
+    e = fx_launch_policy(pol->map_obs[t & 1], pol->map_w1, pol->map_w2, pol->dev, (int)N, pol->k_pad,
+                         io.gumbel ? io.gumbel + (size_t)t * N * 3 : nullptr, io.seed, (unsigned)t, io.actions + (size_t)t * N,
+                         io.logp + (size_t)t * N, io.value + (size_t)t * N, s);
+    if (e != cudaSuccess) return e;
+    e = fx_launch_step(env->P, io.actions + (size_t)t * N, io.obs + (size_t)((t + 1) % slots) * N * D, io.reward + (size_t)t * N,
+                       nullptr, io.done + (size_t)t * N, s, 0, -1, pol->obs16[(t + 1) & 1], pol->k_pad);
+    if (e != cudaSuccess) return e;
+  }
+  return fx_launch_policy(pol->map_obs[H & 1], pol->map_w1, pol->map_w2, pol->dev, (int)N, pol->k_pad, nullptr, io.seed,
+                          (unsigned)H, pol->scratch_act, pol->scratch_logp, io.value + (size_t)H * N, s);
+}
+
+}  // namespace
+
+extern "C" {
+
+int fxenv_policy_destroy(FxPolicy* pol) {
+  if (!pol) return FXENV_OK;
+  DeviceGuard g(pol->env->device);
+  if (pol->cached.exec) cudaGraphExecDestroy(pol->cached.exec);
+  cudaFree(pol->w1); cudaFree(pol->w2); cudaFree(pol->fparams); cudaFree(pol->obs16[0]); cudaFree(pol->obs16[1]);
+  cudaFree(pol->scratch_act); cudaFree(pol->scratch_logp);
+  delete pol;
+  return FXENV_OK;
+}
+
+int fxenv_policy_create(FxEnv* env, FxPolicy** out) {
+  if (!env || !out) return FXENV_E_INVALID;
+  *out = nullptr;
+  if (env->P.cfg.action_mode != FX_ACTION_DISCRETE) return fail(env, FXENV_E_INVALID, "the fused policy samples discrete actions");
+  DeviceGuard g(env->device);
+  FxPolicy* pol = new (std::nothrow) FxPolicy();
+  if (!pol) return fail(env, FXENV_E_NOMEM, "out of host memory");
+  pol->env = env;
+  const size_t N = (size_t)env->P.cfg.num_envs, D = (size_t)env->P.obs_dim;
+  pol->k_pad = (int)((D + 63) / 64 * 64);
+  const size_t KP = (size_t)pol->k_pad, Hd = FX_POLICY_HIDDEN;
+  bool ok = cudaMalloc(&pol->w1, Hd * KP * 2) == cudaSuccess && cudaMalloc(&pol->w2, Hd * Hd * 2) == cudaSuccess &&
+            cudaMalloc(&pol->fparams, (2 * Hd + 4 * Hd + 4) * sizeof(float)) == cudaSuccess &&
+            cudaMalloc(&pol->obs16[0], N * KP * 2) == cudaSuccess && cudaMalloc(&pol->obs16[1], N * KP * 2) == cudaSuccess &&
+            cudaMalloc(&pol->scratch_act, N * 4) == cudaSuccess && cudaMalloc(&pol->scratch_logp, N * 4) == cudaSuccess;
+  if (!ok) { fxenv_policy_destroy(pol); return fail(env, FXENV_E_CUDA, "cudaMalloc(policy buffers) failed"); }
+  // the K padding of the observation copies is never written by the env kernels: zero it once
+  cudaMemset(pol->obs16[0], 0, N * KP * 2);
+  cudaMemset(pol->obs16[1], 0, N * KP * 2);
+  pol->dev.b1 = pol->fparams; pol->dev.b2 = pol->fparams + Hd; pol->dev.head_w = pol->fparams + 2 * Hd;
+  pol->dev.head_b = pol->fparams + 6 * Hd;
+  int rc = make_map(env, &pol->map_obs[0], pol->obs16[0], N, KP, FX_POLICY_TILE_M);
+  if (!rc) rc = make_map(env, &pol->map_obs[1], pol->obs16[1], N, KP, FX_POLICY_TILE_M);
+  if (!rc) rc = make_map(env, &pol->map_w1, pol->w1, Hd, KP, FX_POLICY_HIDDEN);
+  if (!rc) rc = make_map(env, &pol->map_w2, pol->w2, Hd, Hd, FX_POLICY_HIDDEN);
+  if (rc) { fxenv_policy_destroy(pol); return rc; }
+  cudaError_t ce = fx_policy_configure();
+  if (ce != cudaSuccess) { fxenv_policy_destroy(pol); return cuda_fail(env, ce, "fx_policy_configure"); }
+  *out = pol;
+  return FXENV_OK;
+}
+
+int fxenv_policy_set_weights(FxPolicy* pol, const FxPolicyWeights* w, void* stream_) {
+  if (!pol || !w) return FXENV_E_INVALID;
+  FxEnv* env = pol->env;
+  if (!w->w1 || !w->b1 || !w->w2 || !w->b2 || !w->w_pi || !w->b_pi || !w->w_v || !w->b_v) return fail(env, FXENV_E_INVALID, "null weight pointer");
+  DeviceGuard g(env->device);
+  cudaStream_t s = (cudaStream_t)stream_;
+  const int D = env->P.obs_dim, Hd = FX_POLICY_HIDDEN;
+  FX_CUDA(env, fx_policy_pack(w->w1, pol->w1, Hd, D, pol->k_pad, s));
+  FX_CUDA(env, fx_policy_pack(w->w2, pol->w2, Hd, Hd, Hd, s));
+  float* f = pol->fparams;
+  FX_CUDA(env, cudaMemcpyAsync(f, w->b1, Hd * 4, cudaMemcpyDeviceToDevice, s));
+  FX_CUDA(env, cudaMemcpyAsync(f + Hd, w->b2, Hd * 4, cudaMemcpyDeviceToDevice, s));
+  FX_CUDA(env, cudaMemcpyAsync(f + 2 * Hd, w->w_pi, 3 * Hd * 4, cudaMemcpyDeviceToDevice, s));
+  FX_CUDA(env, cudaMemcpyAsync(f + 5 * Hd, w->w_v, Hd * 4, cudaMemcpyDeviceToDevice, s));
+  FX_CUDA(env, cudaMemcpyAsync(f + 6 * Hd, w->b_pi, 3 * 4, cudaMemcpyDeviceToDevice, s));
+  FX_CUDA(env, cudaMemcpyAsync(f + 6 * Hd + 3, w->b_v, 4, cudaMemcpyDeviceToDevice, s));
+  env->launches += 2;
+  pol->has_weights = true;
+  return FXENV_OK;
+}
+
+int fxenv_rollout(FxEnv* env, FxPolicy* pol, const FxRollout* io, void* stream_) {
+  int rc = require_ready(env, true);
+  if (rc) return rc;
+  if (!pol || !io || pol->env != env) return fail(env, FXENV_E_INVALID, "policy does not belong to this env");
+  if (!pol->has_weights) return fail(env, FXENV_E_STATE, "fxenv_policy_set_weights has not been called");
+  if (io->horizon < 1 || io->obs_slots < 2) return fail(env, FXENV_E_INVALID, "horizon must be >= 1 and obs_slots >= 2");
+  if (!io->obs || !io->actions || !io->logp || !io->value || !io->reward || !io->done) return fail(env, FXENV_E_INVALID, "null I/O pointer");
+  DeviceGuard g(env->device);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int64_t nl = 2 * (int64_t)io->horizon + 2;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (stream != nullptr) cudaStreamIsCapturing(stream, &cs);
+  if (cs != cudaStreamCaptureStatusNone || stream == nullptr || (env->P.debug & 32)) {  // inside a capture / legacy stream: plain launches
+    FX_CUDA(env, enqueue_rollout(env, pol, *io, stream));
+    env->launches += nl;
+    return FXENV_OK;
+  }
+  if (!pol->cached.exec || memcmp(&pol->cached.io, io, sizeof(FxRollout)) != 0) {
+    if (pol->cached.exec) { cudaGraphExecDestroy(pol->cached.exec); pol->cached.exec = nullptr; }
+    cudaGraph_t graph = nullptr;
+    FX_CUDA(env, cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+    cudaError_t e = enqueue_rollout(env, pol, *io, stream);
+    cudaError_t e2 = cudaStreamEndCapture(stream, &graph);
+    if (e != cudaSuccess) { if (graph) cudaGraphDestroy(graph); return cuda_fail(env, e, "capture: rollout"); }
+    if (e2 != cudaSuccess) return cuda_fail(env, e2, "cudaStreamEndCapture");
+    e = cudaGraphInstantiate(&pol->cached.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { pol->cached.exec = nullptr; return cuda_fail(env, e, "cudaGraphInstantiate"); }
+    pol->cached.io = *io;
+  }
+  FX_CUDA(env, cudaGraphLaunch(pol->cached.exec, stream));
+  env->launches += nl;
+  return FXENV_OK;
 }
 
 }  // extern "C"

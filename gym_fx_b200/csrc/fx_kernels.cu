@@ -23,6 +23,7 @@
 //
 // Reference call stack being replaced: app/env.py:131-172 -> app/bt_bridge.py:119-150 -> strategy / reward /
 // preprocessor plugins + backtrader (per-function citations in fx_core.cuh).
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
 #include "fx_kernels.cuh"
@@ -170,6 +171,20 @@ __device__ __forceinline__ bool fx_prepare_stats(const FxKernelParams& P, const 
   return true;
 }
 
+// Optional second copy of the observation row in bfloat16 (round-to-nearest-even of the float32 value), K-padded row
+// stride: the A operand of the fused policy kernel (fx_policy.cu).  o16 == nullptr: not requested.
+__device__ __forceinline__ void fx_st16(uint16_t* o16, int j, float v) {
+  if (o16) o16[j] = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+}
+__device__ __forceinline__ void fx_st16x4(uint16_t* o16, int j, float4 v) {  // j % 4 == 0, row 8-byte aligned
+  if (o16) {
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<const uint32_t*>(&lo); u.y = *reinterpret_cast<const uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(o16 + j) = u;
+  }
+}
+
 // ---- observation windows: preprocessor.make_observation (features | prices | returns) in the flat VecEnv layout ----
 // `win` = the staged rows [left, s) (shift already applied): element (k, col) at win[k * C + col].
 // float32 finishing of one feature value: np.clip then np.nan_to_num (feature_window_preprocessor.py:119-123)
@@ -183,10 +198,11 @@ __device__ __forceinline__ float fx_finish_t(float v, float clipf) {
 }
 
 // LONG: windows of several hundred rows, where loop overhead outweighs instruction-cache footprint (the loops are unrolled)
-template <bool FAST5, bool CLIP, bool TAME, bool LONG>
+template <bool FAST5, bool CLIP, bool TAME, bool LONG, bool O16>
 __device__ __noinline__ void fx_emit_windows_t(const FxKernelParams& P, int lane, int s, bool scale,
                                                const double* __restrict__ win, const double* sstat,
-                                               float* __restrict__ out) {
+                                               float* __restrict__ out, uint16_t* __restrict__ o16_) {
+  uint16_t* __restrict__ const o16 = O16 ? o16_ : nullptr;  // O16 == false: the bf16 copy is compiled out
   const FxConfig& c = P.cfg;
   const int W = c.window_size, C = c.n_cols;
   int left = s - W;
@@ -215,7 +231,8 @@ __device__ __noinline__ void fx_emit_windows_t(const FxKernelParams& P, int lane
           float2 v;                                                         \
           v.x = fx_finish_t<CLIP, TAME>((float)((x0 - m0) * r0), clipf);    \
           v.y = fx_finish_t<CLIP, TAME>((float)((x1 - m1) * r1), clipf);    \
-          __stcs(reinterpret_cast<float2*>(out) + q, v);
+          __stcs(reinterpret_cast<float2*>(out) + q, v);                    \
+          fx_st16(o16, 2 * q, v.x); fx_st16(o16, 2 * q + 1, v.y);
         if (LONG) {
 #pragma unroll 4
           for (int q = lane; q < npair; q += 30) { FX_PAIR_BODY }
@@ -228,7 +245,9 @@ __device__ __noinline__ void fx_emit_windows_t(const FxKernelParams& P, int lane
           const int j = total - 1, f = j % 5;
           const bool z = scale && !c.feature_binary[f];
           const double x = win[j];
-          __stcs(out + j, fx_finish_t<CLIP, TAME>(z ? (float)((x - sstat[2 * f]) * sstat[2 * f + 1]) : (float)x, clipf));
+          const float vt = fx_finish_t<CLIP, TAME>(z ? (float)((x - sstat[2 * f]) * sstat[2 * f + 1]) : (float)x, clipf);
+          __stcs(out + j, vt);
+          fx_st16(o16, j, vt);
         }
       }
     } else {
@@ -240,7 +259,9 @@ __device__ __noinline__ void fx_emit_windows_t(const FxKernelParams& P, int lane
         if (k < 0) k = 0;
         const double x = win[k * C + c.feature_cols[f]];
         const float v = (scale && !c.feature_binary[f]) ? (float)((x - sstat[2 * f]) * sstat[2 * f + 1]) : (float)x;
-        __stcs(out + j, fx_finish_t<CLIP, TAME>(v, clipf));
+        const float vf = fx_finish_t<CLIP, TAME>(v, clipf);
+        __stcs(out + j, vf);
+        fx_st16(o16, j, vf);
         w += dw; f += df;
         if (f >= F) { f -= F; w += 1; }
       }
@@ -258,8 +279,10 @@ __device__ __noinline__ void fx_emit_windows_t(const FxKernelParams& P, int lane
       if (k1 < 0) k1 = 0;                                                   \
       const double p = win[k * C + pc];                                     \
       const double prev = win[k1 * C + pc];                                 \
+      const float rt = (w == 0) ? 0.0f : (float)(p - prev);                 \
       __stcs(op + w, (float)p);                                             \
-      __stcs(op + W + w, (w == 0) ? 0.0f : (float)(p - prev));
+      __stcs(op + W + w, rt);                                               \
+      fx_st16(o16, off + w, (float)p); fx_st16(o16, off + W + w, rt);
     if (LONG) {
 #pragma unroll 4
       for (int w = lane; w < W; w += 32) { FX_PRICE_BODY }
@@ -276,9 +299,10 @@ __device__ __noinline__ void fx_emit_windows_t(const FxKernelParams& P, int lane
 // features are (4 * (lane % 5) + i) % 5 in every iteration, so their scale factors stay in registers, and a z-score is
 // ONE fp64 fma, x * (1/std) + (-mean / std) (the reference computes (x - mean) / std in fp64 and casts to float32; the
 // difference is far below half a float32 ulp).  prices | returns: a lane owns 4 consecutive rows.
-template <bool CLIP, bool TAME>
+template <bool CLIP, bool TAME, bool O16>
 __device__ __noinline__ void fx_emit_fast5_q(const FxKernelParams& P, int lane, bool scale, const double* __restrict__ win,
-                                             const double* sstat, float* __restrict__ out) {
+                                             const double* sstat, float* __restrict__ out, uint16_t* __restrict__ o16_) {
+  uint16_t* __restrict__ const o16 = O16 ? o16_ : nullptr;
   const FxConfig& c = P.cfg;
   const int W = c.window_size;
   const float clipf = (float)c.feature_clip;
@@ -303,6 +327,7 @@ __device__ __noinline__ void fx_emit_fast5_q(const FxKernelParams& P, int lane, 
       v.z = fx_finish_t<CLIP, TAME>((float)fma(x[2], r[2], a[2]), clipf);
       v.w = fx_finish_t<CLIP, TAME>((float)fma(x[3], r[3], a[3]), clipf);
       __stcs(o4 + q, v);
+      fx_st16x4(o16, 4 * q, v);
     }
   }
   const int pc = c.price_col;
@@ -317,36 +342,39 @@ __device__ __noinline__ void fx_emit_fast5_q(const FxKernelParams& P, int lane, 
     rv.x = (w0 > 0) ? (float)(p0 - pm) : 0.0f; rv.y = (float)(p1 - p0); rv.z = (float)(p2 - p1); rv.w = (float)(p3 - p2);
     __stcs(reinterpret_cast<float4*>(op + w0), pv);
     __stcs(reinterpret_cast<float4*>(op + W + w0), rv);
+    fx_st16x4(o16, 5 * W + w0, pv);
+    fx_st16x4(o16, 6 * W + w0, rv);
   }
 }
 
-template <bool FAST5>
+template <bool FAST5, bool O16 = true>
 __device__ __forceinline__ void fx_emit_windows(const FxKernelParams& P, int lane, int s, bool scale,
                                                 const double* __restrict__ win, const double* sstat,
-                                                float* __restrict__ out) {
+                                                float* __restrict__ out, uint16_t* __restrict__ o16 = nullptr) {
   if (FAST5 && s >= P.cfg.window_size && (P.cfg.window_size & 3) == 0 && P.cfg.include_price_window &&
       P.cfg.feature_clip > 0.0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
-    if (P.tame_data) fx_emit_fast5_q<true, true>(P, lane, scale, win, sstat, out);
-    else fx_emit_fast5_q<true, false>(P, lane, scale, win, sstat, out);
+    if (P.tame_data) fx_emit_fast5_q<true, true, O16>(P, lane, scale, win, sstat, out, o16);
+    else fx_emit_fast5_q<true, false, O16>(P, lane, scale, win, sstat, out, o16);
     return;
   }
   const bool lng = P.cfg.window_size >= 384;
   if (P.cfg.feature_clip > 0.0) {
     if (P.tame_data) {
-      if (lng) fx_emit_windows_t<FAST5, true, true, true>(P, lane, s, scale, win, sstat, out);
-      else fx_emit_windows_t<FAST5, true, true, false>(P, lane, s, scale, win, sstat, out);
+      if (lng) fx_emit_windows_t<FAST5, true, true, true, O16>(P, lane, s, scale, win, sstat, out, o16);
+      else fx_emit_windows_t<FAST5, true, true, false, O16>(P, lane, s, scale, win, sstat, out, o16);
     } else {
-      fx_emit_windows_t<FAST5, true, false, false>(P, lane, s, scale, win, sstat, out);
+      fx_emit_windows_t<FAST5, true, false, false, O16>(P, lane, s, scale, win, sstat, out, o16);
     }
   } else {
-    fx_emit_windows_t<FAST5, false, false, false>(P, lane, s, scale, win, sstat, out);
+    fx_emit_windows_t<FAST5, false, false, false, O16>(P, lane, s, scale, win, sstat, out, o16);
   }
 }
 
 // issue + wait + emit in one go (terminated path, observe kernel)
 template <bool FAST5>
 __device__ __forceinline__ void fx_stream_windows(const FxKernelParams& P, const FxPairTable& tb, int env, int lane, int s,
-                                                  int64_t start, const WarpSmem& ws, float* __restrict__ out) {
+                                                  int64_t start, const WarpSmem& ws, float* __restrict__ out,
+                                                  uint16_t* __restrict__ o16 = nullptr) {
   const int W = P.cfg.window_size;
   int left = s - W;
   if (left < 0) left = 0;
@@ -355,7 +383,7 @@ __device__ __forceinline__ void fx_stream_windows(const FxKernelParams& P, const
   const int shift = fx_window_issue(tb, P.cfg.n_cols, start, left, s - left, lane, ws);
   const bool scale = fx_prepare_stats(P, tb, env, lane, s, start, ws.stat);
   fx_window_wait(ws);
-  fx_emit_windows<FAST5>(P, lane, s, scale, ws.win + shift, ws.stat, out);
+  fx_emit_windows<FAST5>(P, lane, s, scale, ws.win + shift, ws.stat, out, o16);
 }
 
 __device__ __forceinline__ int fx_scalar_offset(const FxConfig& c) {
@@ -367,7 +395,7 @@ __device__ __forceinline__ int fx_scalar_offset(const FxConfig& c) {
 // the 4 agent scalars at the end of the row (one lane)
 // `last` = price_column of the last window row (local row bar_index - 1)
 __device__ __forceinline__ void fx_write_scalars(const FxKernelParams& P, const FxEnvRegs& e, int32_t total_bars,
-                                                 double last, float* __restrict__ out) {
+                                                 double last, float* __restrict__ out, uint16_t* __restrict__ o16 = nullptr) {
   const FxConfig& c = P.cfg;
   const bool inc_agent = (c.preproc == FX_PREPROC_DEFAULT) || c.include_agent_state;
   if (!inc_agent) return;
@@ -377,8 +405,10 @@ __device__ __forceinline__ void fx_write_scalars(const FxKernelParams& P, const 
   else ref = inc_price ? (double)(float)last : e.price;  // feature_window_preprocessor.py:218-222
   float sc[4];
   fx_agent_scalars(c, e, total_bars, ref, P.inv_initial_cash, sc);
-  float* o = out + fx_scalar_offset(c);
+  const int so = fx_scalar_offset(c);
+  float* o = out + so;
   o[0] = sc[0]; o[1] = sc[1]; o[2] = sc[2]; o[3] = sc[3];
+  fx_st16(o16, so, sc[0]); fx_st16(o16, so + 1, sc[1]); fx_st16(o16, so + 2, sc[2]); fx_st16(o16, so + 3, sc[3]);
 }
 
 // ---- Sharpe: lane-parallel evaluation of the deque statistics -----------------------------------------------------
@@ -454,16 +484,18 @@ __device__ __forceinline__ uint32_t fx_apply_op(uint32_t m, uint32_t op) {
 }
 
 // One env-step of one env by one warp (everything between the cross-kernel dependency wait and the release).
-template <int STRAT, int REWARD, bool FAST5>
+template <int STRAT, int REWARD, bool FAST5, bool O16>
 __device__ __forceinline__ void fx_step_env(const FxKernelParams& P, const void* __restrict__ actions, float* __restrict__ obs,
                                             float* __restrict__ reward, double* __restrict__ reward64,
                                             uint8_t* __restrict__ terminated, const int env, const int lane, const WarpSmem& ws,
-                                            const unsigned phase = 0u, const unsigned step_row = 0u, const unsigned obs_slot_row = 0u) {
+                                            const unsigned phase = 0u, const unsigned step_row = 0u, const unsigned obs_slot_row = 0u,
+                                            uint16_t* __restrict__ obs16 = nullptr, const int stride16 = 0) {
   // `actions` / `reward` / `terminated` / `obs` are the BASES of the caller's arrays (kernel parameters: they cost no
   // registers); this env-step's element is at index step_row + env (step_row = step * num_envs) and its observation row
   // at obs_slot_row + env (obs_slot_row = slot * num_envs).  Addresses are formed where they are used.
 #define FX_OBS_ROW() (obs + ((size_t)obs_slot_row + (size_t)env) * (size_t)P.obs_dim)
 #define FX_OUT_IDX() ((size_t)step_row + (size_t)env)
+#define FX_OBS_ROW16() ((O16 && obs16) ? obs16 + (size_t)env * (size_t)stride16 : nullptr)  // bf16 copy (single-step kernel only)
   const FxConfig& c = P.cfg;
   const FxDeviceState& st = P.st;
   const int C = c.n_cols;
@@ -552,7 +584,7 @@ __device__ __forceinline__ void fx_step_env(const FxKernelParams& P, const void*
       reward[FX_OUT_IDX()] = 0.0f;
       if (reward64) reward64[FX_OUT_IDX()] = 0.0;
       terminated[FX_OUT_IDX()] = c.auto_reset ? 0 : 1;
-      fx_write_scalars(P, e, total_bars, tb.candles[(start + e.bar_index - 1) * (int64_t)C + c.price_col], FX_OBS_ROW());
+      fx_write_scalars(P, e, total_bars, tb.candles[(start + e.bar_index - 1) * (int64_t)C + c.price_col], FX_OBS_ROW(), FX_OBS_ROW16());
     }
     {
       const int s = e.bar_index;
@@ -562,7 +594,7 @@ __device__ __forceinline__ void fx_step_env(const FxKernelParams& P, const void*
       const int shift = fx_window_issue(tb, C, start, left, s - left, lane, ws);
       const bool scale = fx_prepare_stats(P, tb, env, lane, s, start, ws.stat);
       fx_window_wait(ws, phase);
-      fx_emit_windows<FAST5>(P, lane, s, scale, ws.win + shift, ws.stat, FX_OBS_ROW());
+      fx_emit_windows<FAST5, O16>(P, lane, s, scale, ws.win + shift, ws.stat, FX_OBS_ROW(), FX_OBS_ROW16());
     }
     return;
   }
@@ -621,7 +653,7 @@ __device__ __forceinline__ void fx_step_env(const FxKernelParams& P, const void*
     __syncwarp();                                                                                          \
     if (!(dbg & 1)) {                                                                                      \
       fx_window_wait(ws, phase);                                                                           \
-      fx_emit_windows<FAST5>(P, lane, s_obs, scale, ws.win + win_shift, ws.stat, FX_OBS_ROW());            \
+      fx_emit_windows<FAST5, O16>(P, lane, s_obs, scale, ws.win + win_shift, ws.stat, FX_OBS_ROW(), FX_OBS_ROW16()); \
     }                                                                                                      \
   } while (0)
 
@@ -823,7 +855,7 @@ __device__ __forceinline__ void fx_step_env(const FxKernelParams& P, const void*
       reward[FX_OUT_IDX()] = (float)r;
       if (reward64) reward64[FX_OUT_IDX()] = r;
       terminated[FX_OUT_IDX()] = term ? 1 : 0;
-      fx_write_scalars(P, e, total_bars, last_price, FX_OBS_ROW());
+      fx_write_scalars(P, e, total_bars, last_price, FX_OBS_ROW(), FX_OBS_ROW16());
     }
   } else {  // timing experiment only (FXENV_DEBUG & 2): cursor only
     if (lane == 0) { st.t[env] = t; st.flags[env] = flags; st.bar_index[env] = t + 1; reward[FX_OUT_IDX()] = 0.f; terminated[FX_OUT_IDX()] = 0; }
@@ -841,6 +873,7 @@ __device__ __forceinline__ void fx_step_env(const FxKernelParams& P, const void*
   FX_STAMP_GLOBAL(11);
 #undef FX_EMIT_OBSERVATION
 #undef FX_OBS_ROW
+#undef FX_OBS_ROW16
 #undef FX_OUT_IDX
 #undef FX_STAMP
 #undef FX_STAMP_DEP
@@ -864,7 +897,7 @@ template <int STRAT, int REWARD, bool FAST5>
 __global__ void __launch_bounds__(FX_WARPS * 32, FX_MIN_BLOCKS)
 fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict__ actions, float* __restrict__ obs,
                float* __restrict__ reward, double* __restrict__ reward64, uint8_t* __restrict__ terminated,
-               const int env_begin, const int env_end) {
+               const int env_begin, const int env_end, uint16_t* __restrict__ obs16, const int stride16) {
   extern __shared__ __align__(16) unsigned char fx_smem[];
   const FxConfig& c = P.cfg;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -876,7 +909,7 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
   asm volatile("griddepcontrol.launch_dependents;");
   fx_window_init(lane, ws);  // mbarrier init + fence
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  fx_step_env<STRAT, REWARD, FAST5>(P, actions, obs, reward, reward64, terminated, env, lane, ws);
+  fx_step_env<STRAT, REWARD, FAST5, true>(P, actions, obs, reward, reward64, terminated, env, lane, ws, 0u, 0u, 0u, obs16, stride16);
 }
 
 // ---- K steps in ONE launch (fxenv_step_many): persistent warps pull (step, env) tickets ----------------------------
@@ -927,7 +960,7 @@ fx_rollout_kernel(const __grid_constant__ FxKernelParams P, const char* __restri
 #ifdef FXENV_ENABLE_TIMING
     if (P.timeline && lane == 0) { long long g__; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g__)); P.timeline[((size_t)k * N + env) * 2] = g__; }
 #endif
-    fx_step_env<STRAT, REWARD, FAST5>(P, actions, obs, reward, nullptr, terminated, (int)env, lane, ws, phase, k * N,
+    fx_step_env<STRAT, REWARD, FAST5, false>(P, actions, obs, reward, nullptr, terminated, (int)env, lane, ws, phase, k * N,
                                       (k % (unsigned)obs_slots) * N);
     __syncwarp();
     if (lane == 0) fx_st_release(P.seq + env, (int)(seq_base + k + 1u));
@@ -975,7 +1008,7 @@ __global__ void fx_reset_kernel(const __grid_constant__ FxKernelParams P, const 
 }
 
 // writes the observation of the current state (what reset() returns): one warp per env
-__global__ void __launch_bounds__(FX_WARPS * 32) fx_observe_kernel(const __grid_constant__ FxKernelParams P, float* __restrict__ obs) {
+__global__ void __launch_bounds__(FX_WARPS * 32) fx_observe_kernel(const __grid_constant__ FxKernelParams P, float* __restrict__ obs, uint16_t* __restrict__ obs16, const int stride16) {
   extern __shared__ __align__(16) unsigned char fx_smem[];
   const FxConfig& c = P.cfg;
   const FxDeviceState& st = P.st;
@@ -994,8 +1027,9 @@ __global__ void __launch_bounds__(FX_WARPS * 32) fx_observe_kernel(const __grid_
   if (s < 1) s = 1;
   if (s > total_bars) s = total_bars;  // app/env.py:228
   float* row = obs + (int64_t)env * P.obs_dim;
-  if (lane == 0) fx_write_scalars(P, e, total_bars, tb.candles[(start + s - 1) * (int64_t)c.n_cols + c.price_col], row);
-  fx_stream_windows<false>(P, tb, env, lane, s, start, ws, row);
+  uint16_t* row16 = obs16 ? obs16 + (int64_t)env * stride16 : nullptr;
+  if (lane == 0) fx_write_scalars(P, e, total_bars, tb.candles[(start + s - 1) * (int64_t)c.n_cols + c.price_col], row, row16);
+  fx_stream_windows<false>(P, tb, env, lane, s, start, ws, row, row16);
 }
 
 // Per-bar rolling z-score statistics (feature_window_preprocessor._scale_window :96-124 for a FULL window):
@@ -1022,7 +1056,7 @@ __global__ void fx_stats_kernel(FxConfig c, const double* __restrict__ candles, 
   stats[idx * 2 + 1] = rc;
 }
 
-typedef void (*StepKernel)(const FxKernelParams, const void*, float*, float*, double*, uint8_t*, int, int);
+typedef void (*StepKernel)(const FxKernelParams, const void*, float*, float*, double*, uint8_t*, int, int, uint16_t*, int);
 
 template <int STRAT>
 StepKernel pick_reward(int reward, bool fast5) {
@@ -1111,7 +1145,7 @@ cudaError_t fx_configure_kernels(FxKernelParams& P) {
 }
 
 cudaError_t fx_launch_step(const FxKernelParams& P, const void* actions, float* obs, float* reward, double* reward64,
-                           uint8_t* terminated, cudaStream_t stream, int env_begin, int env_end) {
+                           uint8_t* terminated, cudaStream_t stream, int env_begin, int env_end, uint16_t* obs16, int stride16) {
   if (env_end < 0) env_end = P.cfg.num_envs;
   cudaLaunchConfig_t lc = {};
   lc.gridDim = dim3((env_end - env_begin + FX_WARPS - 1) / FX_WARPS);
@@ -1123,7 +1157,7 @@ cudaError_t fx_launch_step(const FxKernelParams& P, const void* actions, float* 
   at[0].val.programmaticStreamSerializationAllowed = 1;
   lc.attrs = at;
   lc.numAttrs = (P.debug & 4) ? 0 : 1;  // FXENV_DEBUG & 4: plain stream-serialised launches (A/B timing only)
-  return cudaLaunchKernelEx(&lc, pick_kernel(P), P, actions, obs, reward, reward64, terminated, env_begin, env_end);
+  return cudaLaunchKernelEx(&lc, pick_kernel(P), P, actions, obs, reward, reward64, terminated, env_begin, env_end, obs16, stride16);
 }
 
 int fx_rollout_blocks(const FxKernelParams& P) {
@@ -1163,9 +1197,9 @@ cudaError_t fx_launch_reset(const FxKernelParams& P, const int64_t* start_bar, c
   return cudaGetLastError();
 }
 
-cudaError_t fx_launch_observe(const FxKernelParams& P, float* obs, cudaStream_t stream) {
+cudaError_t fx_launch_observe(const FxKernelParams& P, float* obs, cudaStream_t stream, uint16_t* obs16, int stride16) {
   const int N = P.cfg.num_envs;
-  fx_observe_kernel<<<(N + FX_WARPS - 1) / FX_WARPS, FX_WARPS * 32, observe_smem_bytes(P), stream>>>(P, obs);
+  fx_observe_kernel<<<(N + FX_WARPS - 1) / FX_WARPS, FX_WARPS * 32, observe_smem_bytes(P), stream>>>(P, obs, obs16, stride16);
   return cudaGetLastError();
 }
 

@@ -76,10 +76,12 @@ struct FxKernelParams {
 // host-callable launchers (fx_kernels.cu)
 // one step of the envs [env_begin, env_end) (env_end < 0: all); the array arguments are the bases for env 0
 cudaError_t fx_launch_step(const FxKernelParams& P, const void* actions, float* obs, float* reward, double* reward64,
-                           uint8_t* terminated, cudaStream_t stream, int env_begin = 0, int env_end = -1);
+                           uint8_t* terminated, cudaStream_t stream, int env_begin = 0, int env_end = -1,
+                           uint16_t* obs16 = nullptr, int stride16 = 0);  // obs16: optional bf16 copy of the rows
 cudaError_t fx_launch_reset(const FxKernelParams& P, const int64_t* start_bar, const uint8_t* mask, int first,
                             cudaStream_t stream);
-cudaError_t fx_launch_observe(const FxKernelParams& P, float* obs, cudaStream_t stream);
+cudaError_t fx_launch_observe(const FxKernelParams& P, float* obs, cudaStream_t stream, uint16_t* obs16 = nullptr,
+                              int stride16 = 0);
 cudaError_t fx_launch_stats(const FxConfig& cfg, const double* candles, double* stats, int64_t T, cudaStream_t stream);
 cudaError_t fx_configure_kernels(FxKernelParams& P);
 cudaError_t fx_launch_rollout(const FxKernelParams& P, const void* actions, float* obs, int obs_slots, float* reward,

@@ -62,6 +62,7 @@ class VecFxEnv:
         self.L.fxenv_get_info(self._h, C.byref(self._info_ptrs))
         self._info_views: Dict[str, torch.Tensor] = {}
         self.action_dtype = torch.float32 if cfg.action_mode == 1 else torch.int32
+        self._policies: list = []
 
     # ------------------------------------------------------------------ lifecycle
     def close(self):
@@ -69,6 +70,8 @@ class VecFxEnv:
             # the info tensors are zero-copy views of the library's state slab, which fxenv_destroy frees: drop the cached
             # ones (views a caller still holds become invalid, like any tensor handed out by info() -- clone to keep)
             self._info_views.clear()
+            for pol in list(getattr(self, "_policies", [])):   # policies hold device buffers tied to this handle
+                pol.close()
             self.L.fxenv_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -269,6 +272,41 @@ class VecFxEnv:
         return {"trades": trades, "sqn": {"sqn": sqn, "trades": closed}, "sharpe": {}, "time_return": {},
                 "drawdown": {"max": {"drawdown": float(rs[R["dd_max_pct"]]), "moneydown": float(rs[R["dd_max_money"]])}}}
 
+    # ------------------------------------------------------------------ closed loop (policy on the device)
+    def make_policy(self, weights=None) -> "FusedPolicy":
+        """An actor-critic MLP(obs_dim, 256, 256) evaluated by the fused tensor-core kernel (fxenv.h: FxPolicy)."""
+        return FusedPolicy(self, weights)
+
+    def rollout(self, policy: "FusedPolicy", horizon: int, buffers: Optional[Dict[str, torch.Tensor]] = None,
+                gumbel: Optional[torch.Tensor] = None, seed: int = 0) -> Dict[str, torch.Tensor]:
+        """`horizon` closed-loop steps (policy -> sample -> env.step) from the current state, all on the device: the
+        loop of the reference's driver (app/main.py:57-65) with a learned policy.  Returns / fills `buffers`:
+        obs [H+1, N, D] (obs[t] is what the policy saw at step t), actions int32 [H, N], logp [H, N], value [H+1, N]
+        (value[H] bootstraps), reward [H, N], done uint8 [H, N].  gumbel: optional float32 [H, N, 3] Gumbel(0,1) noise
+        (reproducible sampling); default: the kernel's counter-based generator seeded with `seed`."""
+        H, N, D, dev = int(horizon), self.num_envs, self.obs_dim, self.device
+        b = buffers if buffers is not None else {}
+        want = {"obs": ((H + 1, N, D), torch.float32), "actions": ((H, N), torch.int32), "logp": ((H, N), torch.float32),
+                "value": ((H + 1, N), torch.float32), "reward": ((H, N), torch.float32), "done": ((H, N), torch.uint8)}
+        for k, (shape, dt) in want.items():
+            if k not in b:
+                b[k] = torch.empty(shape, dtype=dt, device=dev)
+            elif k == "obs":
+                if b[k].dim() != 3 or b[k].shape[0] < 2:
+                    raise ValueError("obs must be [slots >= 2, num_envs, obs_dim]")
+                self._check("obs", b[k], dt, (int(b[k].shape[0]), N, D))
+            else:
+                self._check(k, b[k], dt, shape)
+        if gumbel is not None:
+            self._check("gumbel", gumbel, torch.float32, (H, N, 3))
+        io = _native.FxRollout(H, int(b["obs"].shape[0]), b["obs"].data_ptr(), b["actions"].data_ptr(), b["logp"].data_ptr(),
+                               b["value"].data_ptr(), b["reward"].data_ptr(), b["done"].data_ptr(),
+                               0 if gumbel is None else gumbel.data_ptr(), int(seed) & (2**64 - 1))
+        rc = self.L.fxenv_rollout(self._h, policy._p, C.byref(io), self._stream())
+        _native.check(self.L, self._h, rc, "fxenv_rollout")
+        policy._keep = (b, gumbel)
+        return b
+
     def launch_count(self) -> int:
         return int(self.L.fxenv_launch_count(self._h))
 
@@ -323,3 +361,56 @@ def _tensor_from_ptr(ptr: int, n: int, dtype: torch.dtype, device: torch.device)
     typestr = {torch.float64: "<f8", torch.int32: "<i4", torch.int64: "<i8", torch.uint8: "|u1"}[dtype]
     with torch.cuda.device(device):
         return torch.as_tensor(_CudaArrayView(ptr, n, typestr), device=device)
+
+
+class FusedPolicy:
+    """Device-resident actor-critic MLP(obs_dim, 256, 256) -> 3 logits + value, evaluated between env steps by the fused
+    tcgen05 kernel (gym_fx_b200/csrc/fx_policy.cu).  `set_weights` takes float32 CUDA tensors in torch.nn.Linear layout
+    (or a module with .body[0], .body[2], .pi, .v like examples/ppo_rollout.py's ActorCritic)."""
+
+    HIDDEN = 256
+
+    def __init__(self, env: VecFxEnv, weights=None):
+        self.env = env
+        self._p = C.c_void_p()
+        rc = env.L.fxenv_policy_create(env._h, C.byref(self._p))
+        _native.check(env.L, env._h, rc, "fxenv_policy_create")
+        self._keep = None
+        env._policies.append(self)
+        if weights is not None:
+            self.set_weights(weights)
+
+    def set_weights(self, weights):
+        if not isinstance(weights, dict):
+            m = weights
+            weights = {"w1": m.body[0].weight, "b1": m.body[0].bias, "w2": m.body[2].weight, "b2": m.body[2].bias,
+                       "w_pi": m.pi.weight, "b_pi": m.pi.bias, "w_v": m.v.weight, "b_v": m.v.bias}
+        D, Hd = self.env.obs_dim, self.HIDDEN
+        shapes = {"w1": (Hd, D), "b1": (Hd,), "w2": (Hd, Hd), "b2": (Hd,), "w_pi": (3, Hd), "b_pi": (3,), "w_v": (Hd,), "b_v": (1,)}
+        ts = {}
+        for k, shape in shapes.items():
+            t = weights[k].detach()
+            if k == "w_v":
+                t = t.reshape(-1)
+            t = t.to(device=self.env.device, dtype=torch.float32).contiguous()
+            if tuple(t.shape) != shape:
+                raise ValueError(f"{k} must have shape {shape}, got {tuple(t.shape)}")
+            ts[k] = t
+        w = _native.FxPolicyWeights(*[ts[k].data_ptr() for k in ("w1", "b1", "w2", "b2", "w_pi", "b_pi", "w_v", "b_v")])
+        rc = self.env.L.fxenv_policy_set_weights(self._p, C.byref(w), self.env._stream())
+        _native.check(self.env.L, self.env._h, rc, "fxenv_policy_set_weights")
+        self._w = ts  # keep the sources alive until the stream-ordered copies have run
+
+    def close(self):
+        if self._p:
+            self.env.L.fxenv_policy_destroy(self._p)
+            self._p = C.c_void_p()
+            if self in self.env._policies:
+                self.env._policies.remove(self)
+
+    def __del__(self):
+        try:
+            if self.env._h:
+                self.close()
+        except Exception:
+            pass

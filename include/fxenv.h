@@ -231,6 +231,55 @@ int fxenv_set_state(FxEnv* env, const void* buf_host, int64_t nbytes);
 /* Kernels launched by this handle since creation (bench.py's gpu_launches). */
 int64_t fxenv_launch_count(const FxEnv* env);
 
+/* ---- closed loop: a policy on the device between the steps ------------------------------------------------------
+ * Replaces the caller loop of app/main.py:57-65 (`action = strategy.decide_action(obs, info, step); env.step(action)`)
+ * for a learned actor-critic (BASELINE configs[3]: PPO MLP(256,256)): observation rows never leave the GPU, and the
+ * policy is one fused tensor-core kernel per step (tcgen05 / TMEM / TMA, gym_fx_b200/csrc/fx_policy.cu), chained to the
+ * env step kernel by programmatic dependent launches.  Discrete action mode only.
+ *
+ *   h1 = tanh(obs W1^T + b1), h2 = tanh(h1 W2^T + b2), logits = h2 Wpi^T + bpi (3), value = h2 wv + bv
+ *   action = argmax(logits + Gumbel noise), logp = log_softmax(logits)[action]
+ * The two hidden layers run in bfloat16 with float32 accumulation (the env step writes a bfloat16 copy of each row for
+ * this purpose); biases, heads, sampling and log-prob in float32. */
+typedef struct FxPolicy FxPolicy;
+
+/* DEVICE pointers to float32 parameters in torch.nn.Linear layout ([out][in] row-major). */
+typedef struct FxPolicyWeights {
+  const float* w1;   /* [256][obs_dim] */
+  const float* b1;   /* [256] */
+  const float* w2;   /* [256][256] */
+  const float* b2;   /* [256] */
+  const float* w_pi; /* [3][256] */
+  const float* b_pi; /* [3] */
+  const float* w_v;  /* [256] */
+  const float* b_v;  /* [1] */
+} FxPolicyWeights;
+
+/* Buffers of one rollout of `horizon` steps (all DEVICE, caller-owned).  Step t: the policy reads the observation of
+ * slot t % obs_slots, writes actions/logp/value at [t], the env step writes reward/done at [t] and the next observation
+ * into slot (t + 1) % obs_slots; value[horizon] is the value of the last observation (bootstrap).  obs_slots >= 2
+ * (horizon + 1 keeps every observation for the learner). */
+typedef struct FxRollout {
+  int32_t horizon;
+  int32_t obs_slots;
+  float* obs;           /* [obs_slots][num_envs][obs_dim] */
+  int32_t* actions;     /* [horizon][num_envs] */
+  float* logp;          /* [horizon][num_envs] */
+  float* value;         /* [horizon + 1][num_envs] */
+  float* reward;        /* [horizon][num_envs] */
+  uint8_t* done;        /* [horizon][num_envs] */
+  const float* gumbel;  /* [horizon][num_envs][3] Gumbel(0,1) noise, or NULL: counter-based generator from `seed` */
+  uint64_t seed;
+} FxRollout;
+
+int fxenv_policy_create(FxEnv* env, FxPolicy** out);
+/* Converts / copies the parameters into the policy's own device buffers (stream-ordered; call after every optimiser step). */
+int fxenv_policy_set_weights(FxPolicy* pol, const FxPolicyWeights* weights_dev, void* stream);
+int fxenv_policy_destroy(FxPolicy* pol);
+/* `horizon` closed-loop steps starting from the env's current state; everything is enqueued on `stream`
+ * (2 * horizon + 2 kernels; the launch sequence is cached as a CUDA graph per buffer set). */
+int fxenv_rollout(FxEnv* env, FxPolicy* pol, const FxRollout* io, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
