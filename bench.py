@@ -19,6 +19,9 @@ ours:       K steps through fxenv_step_many in batches of <= 500 (actions pre-ge
             the actions from pinned memory, the kernel, D2H of obs/reward/terminated, host sync.
             `roofline` = algorithmic bytes per launch / average launch duration vs measured HBM peak.
             `cpu_baseline` = the C oracle port timed on this box's host cores (rank 0, N=1, bounded sample).
+            `closed_loop` = BASELINE configs[3] shape with the policy IN the loop (fused tcgen05 actor-critic kernel <->
+            env step, VecFxEnv.rollout) and one PPO update with its NCCL all-reduces (time per update and share).
+            `other_workloads` (N=1) = short runs of BASELINE configs[2] and configs[4] (cfg3 / cfg5 shapes).
 reference:  the CPU arm: the oracle port (oracle/fxenv_oracle.c; the Python reference cannot travel to the GPU box)
             stepping the SAME workload with all host threads.
 """
@@ -282,6 +285,106 @@ def single_step_graph_rate(args, cfg, candles, minutes, N, starts, acts, ring, r
             "note": "CUDA graph of single-step launches (grid-wide dependency between steps, programmatic dependent launch)"}
 
 
+def short_workload_rate(name, K, dev):
+    """`other_workloads`: a short device-resident run (K steps after 3 warm-up steps, same rules as the main measurement)
+    of another BASELINE shape on this GPU: value / us per step / roofline fraction / engine."""
+    import torch
+    from gym_fx_b200.sharding import shard_starts
+    from gym_fx_b200.vec_env import VecFxEnv
+
+    cfg, candles, minutes, N, D, algo_bytes, desc = build_workload(name)
+    env = VecFxEnv(cfg, candles, minutes, device=dev)
+    env.reset(torch.as_tensor(shard_starts(N, 0, 1, T_BARS, 2 * K + 64, 256)))
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(4321)
+    acts = torch.randint(0, 3, (K, N), generator=gen, device=dev, dtype=torch.int32)
+    slots = max(2, -(-int(L2_BYTES * 1.8) // (N * D * 4)))
+    ring = torch.empty((slots, N, D), dtype=torch.float32, device=dev)
+    rews = torch.empty((K, N), dtype=torch.float32, device=dev)
+    terms = torch.empty((K, N), dtype=torch.uint8, device=dev)
+    plan = env.plan_step_many(acts, ring, rews, terms)
+    plan()                                   # warm-up: K >= 3 steps, instantiates the graph if that engine is used
+    torch.cuda.synchronize(dev)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    plan()
+    ev1.record()
+    torch.cuda.synchronize(dev)
+    ms = ev0.elapsed_time(ev1)
+    peak, _ = measured_peak_gbs()
+    out = {"workload": desc, "value": N * K / (ms * 1e-3), "unit": "env-steps/s", "ms_per_step": ms / K, "steps": K,
+           "engine": env.step_many_engine(K), "roofline_frac": N * algo_bytes / (ms * 1e-3 / K) / 1e9 / peak,
+           "order_overflow_envs": int((env.info()["flags"] & 16).ne(0).sum().item())}
+    env.close()
+    del ring
+    torch.cuda.empty_cache()
+    return out
+
+
+def closed_loop_block(K, rank, world, dev, dist):
+    """BASELINE configs[3]: 4096 envs/GPU (W=128, fixed SL/TP, sharpe_reward) with a PPO actor-critic MLP(256,256) IN the
+    loop -- the fused tcgen05 policy kernel between the env steps (VecFxEnv.rollout) -- followed by one PPO update whose
+    gradients / advantage statistics cross the ranks by NCCL all-reduce.  Device time, max over ranks."""
+    import torch
+    from gym_fx_b200.learner import ActorCritic, ppo_update
+    from gym_fx_b200.sharding import shard_starts
+    from gym_fx_b200.vec_env import VecFxEnv
+
+    cfg, candles, minutes, N, D, _, desc = build_workload("cfg4")
+    env = VecFxEnv(cfg, candles, minutes, device=dev)
+    H = max(2, min(32, K))
+    reps = max(1, min(8, K // H))
+    env.reset(torch.as_tensor(shard_starts(N, rank, world, T_BARS, (reps + 3) * H + 64, 256)))
+    torch.manual_seed(0)                                     # identical replicas on every rank
+    torch.backends.cuda.matmul.allow_tf32 = True
+    net = ActorCritic(D).to(dev)
+    opt = torch.optim.Adam(net.parameters(), lr=3e-4, eps=1e-5)
+    pol = env.make_policy(net)
+    buf = env.rollout(pol, H, seed=rank)                     # warm-up (instantiates the graph), also the learner's batch
+    env.rollout(pol, H, buffers=buf, seed=rank + 1000)
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for r in range(reps):
+        env.rollout(pol, H, buffers=buf, seed=rank + 2000 + r)
+    ev1.record()
+    torch.cuda.synchronize(dev)
+    roll_ms = ev0.elapsed_time(ev1) / reps
+    prev_done = torch.zeros(N, dtype=torch.uint8, device=dev)
+    ppo_update(net, opt, buf, prev_done, dist, epochs=1, minibatches=4)      # warm-up (cuBLAS handles, NCCL channels)
+    timers = {}
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    u0.record()
+    stats = ppo_update(net, opt, buf, prev_done, dist, epochs=1, minibatches=4, timers=timers)
+    pol.set_weights(net)                                     # new parameters for the next rollout (bf16 repack)
+    u1.record()
+    torch.cuda.synchronize(dev)
+    upd_ms = u0.elapsed_time(u1)
+    ar_ms = sum(a.elapsed_time(b) for a, b in timers.get("allreduce", []))
+    t = torch.tensor([roll_ms, upd_ms, ar_ms], dtype=torch.float64, device=dev)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    roll_ms, upd_ms, ar_ms = (float(x) for x in t)
+    n_params = sum(p.numel() for p in net.parameters())
+    env.close()
+    return {
+        "workload": desc, "policy": f"actor-critic MLP({D},256,256)+3 logits+value, fused tcgen05 kernel (bf16 x bf16 -> fp32), Gumbel-max sampling in-kernel",
+        "horizon": H, "rollouts_timed": reps, "value": N * world * H / (roll_ms * 1e-3), "unit": "env-steps/s",
+        "ms_per_step": roll_ms / H, "kernels_per_step": 2,
+        "learner": {"update": "PPO, 1 epoch x 4 minibatches, torch autograd (tf32), Adam", "update_ms": upd_ms,
+                    "allreduce_ms_per_update": ar_ms, "allreduce_share_of_update": ar_ms / upd_ms if upd_ms > 0 else None,
+                    "allreduce_calls_per_update": len(timers.get("allreduce", [])),
+                    "grad_bucket_bytes": n_params * 4, "advantage_stats_bytes": 24,
+                    "collective": "NCCL all-reduce (flat gradient bucket per minibatch + [sum, sumsq, count] once)" if dist else "none (1 GPU)",
+                    "train_value": N * world * H / ((roll_ms + upd_ms) * 1e-3), **stats},
+    }
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     from gym_fx_b200.sharding import check_pair_alignment, shard_starts
@@ -424,8 +527,25 @@ def run_ours(args, rank, world, local_rank):
             line["cpu_baseline"] = {"value": rate, "unit": "env-steps/s", "cores": used, "kind": "port",
                                     "sample": f"{sample_envs} envs x {done} steps ({dt:.1f} s), C oracle port, {used} host threads, "
                                               f"no per-step barrier"}
-        emit_json(line)
     env.close()
+    del ring
+    torch.cuda.empty_cache()
+    extra = {}
+    if not args.no_closed_loop:
+        try:
+            extra["closed_loop"] = closed_loop_block(K, rank, world, dev, dist)
+        except Exception as exc:   # the headline line must survive a failure of an auxiliary block -- but say so
+            extra["closed_loop"] = {"error": f"{type(exc).__name__}: {exc}"}
+    if rank == 0:
+        if world == 1 and not args.no_other_workloads:
+            extra["other_workloads"] = {}
+            for name in ("cfg3", "cfg5"):
+                try:
+                    extra["other_workloads"][name] = short_workload_rate(name, max(3, min(K, 100)), dev)
+                except Exception as exc:
+                    extra["other_workloads"][name] = {"error": f"{type(exc).__name__}: {exc}"}
+        line.update(extra)
+        emit_json(line)
     if dist:
         dist.barrier()
         dist.destroy_process_group()
@@ -463,6 +583,8 @@ def main():
     ap.add_argument("--envs", type=int, default=None, help="envs per GPU (default: the workload's)")
     ap.add_argument("--no-single-step", action="store_true", help="skip the single-step-graph reference measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-closed-loop", action="store_true", help="skip the policy-in-the-loop (cfg4) block")
+    ap.add_argument("--no-other-workloads", action="store_true", help="skip the short cfg3 / cfg5 runs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
