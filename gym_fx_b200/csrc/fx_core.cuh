@@ -201,9 +201,12 @@ FX_HD void fx_rs_trade(const RS& rs, double oldsize, double closed, double opene
     }
   }
   if (opened != 0.0) {
-    const double tsize = oldsize + closed;
+    const double tsize = oldsize + closed, nsize = tsize + opened;
     tcomm += openedcomm;
-    tprice = (tsize * tprice + opened * price) / (tsize + opened);
+    // Trade.update decides by |size after| > |size before|: an opening bit too small to change the size (absorbed by
+    // rounding, e.g. the close() of a 1e-12 dust position executing after the position has flipped) books a pnl instead
+    if (fabs(nsize) > fabs(tsize)) tprice = (tsize * tprice + opened * price) / nsize;
+    else tpnl += (-opened) * (price - tprice);
     if (tsize == 0.0) rs.set(FX_RS_OPENED, rs.get(FX_RS_OPENED) + 1.0);  // trade.justopened
   }
   rs.set(FX_RS_TR_PRICE, tprice); rs.set(FX_RS_TR_PNL, tpnl); rs.set(FX_RS_TR_COMM, tcomm);

@@ -146,7 +146,8 @@ class OracleVec:
         return {k: np.asarray(v, dt.get(k, np.float64)) for k, v in out.items()}
 
     SUMMARY_FIELDS = ("max_drawdown_pct", "max_drawdown_money", "trades_total", "trades_won", "trades_lost",
-                      "avg_trade_pnl", "sqn", "trades_closed")
+                      "avg_trade_pnl", "sqn", "trades_closed", "open_trade_size", "open_trade_price", "open_trade_pnl",
+                      "open_trade_commission")
 
     def summary(self):
         """Analyzer-derived fields of metrics_plugins/default_metrics.py:48-60, one array per field (NaN = None)."""

@@ -72,3 +72,40 @@ def test_product_core_matches_oracle_on_random_configs(seed):
     if closed > 1 and osum["sqn"] == osum["sqn"]:
         sqn = np.sqrt(closed) * rs[7] / np.sqrt(rs[8] / closed)
         np.testing.assert_allclose(sqn, osum["sqn"], rtol=1e-9, err_msg=f"seed {seed}: sqn")
+
+
+def test_trade_statistics_with_dust_positions():
+    """rel_volume sizing gives non-round order sizes: closing a position leaves 1e-12 'dust', whose own close() order can
+    execute after the position has flipped and be absorbed by rounding -- backtrader's Trade.update then books a pnl
+    instead of averaging the price (|size after| > |size before| is false).  192 envs, product core vs oracle analyzers."""
+    from gym_fx_b200.synth import start_offsets
+    cfgd = {**S.DEFAULTS, "window_size": 16, "commission": 2e-5, "leverage": 5.0, "rel_volume": 0.3, "max_order_volume": 9000.0}
+    pl = S.build_mirror_plugins(cfgd, {**S.DEFAULT_PLUGINS, "strategy": "direct_atr_sltp"})
+    N, T, steps = 192, 6000, 330
+    mk = lambda n: lower_config(cfgd, broker_plugin=pl["broker"], strategy_plugin=pl["strategy"], preprocessor_plugin=pl["preprocessor"],
+                                reward_plugin=pl["reward"], columns=S.OHLCV, num_envs=n, order_capacity=512)
+    candles, minutes = synth_candles(T, 0), synth_minutes(T)
+    starts = start_offsets(N, T, steps + 10, 300)
+    orc = OracleVec(mk(N), [candles], [minutes])
+    orc.reset(starts)
+    cores = [HostSimEnv(mk(1), candles, minutes) for _ in range(N)]
+    for i, h in enumerate(cores):
+        h.reset(int(starts[i]))
+    rng = np.random.default_rng(2024)
+    dust = 0
+    for k in range(steps):
+        a = rng.integers(0, 3, N).astype(np.int32)
+        orc.step(a, want_obs=False)
+        for i, h in enumerate(cores):
+            h.step(int(a[i]))
+        if k % 4 == 0:
+            ps = np.abs(orc.info()["position_size"])
+            dust += int(np.count_nonzero((ps > 0.0) & (ps < 1e-6)))
+    osum = orc.summary()
+    for i, h in enumerate(cores):
+        rs, closed = h.stats(), h.info()["trades"]
+        assert (rs[9], rs[10], rs[11], closed) == (osum["trades_total"][i], osum["trades_won"][i], osum["trades_lost"][i], osum["trades_closed"][i]), i
+        assert rs[2] == osum["max_drawdown_pct"][i] and rs[1] == osum["max_drawdown_money"][i], i
+        if closed:
+            assert rs[6] / closed == osum["avg_trade_pnl"][i], (i, rs[6] / closed, osum["avg_trade_pnl"][i])
+    assert dust > 0, "the scenario no longer produces dust positions"
