@@ -478,23 +478,56 @@ int fxenv_get_info(FxEnv* env, FxInfoPtrs* out) {
   return FXENV_OK;
 }
 
-int64_t fxenv_state_bytes(const FxEnv* env) { return env ? (int64_t)env->slab_bytes : -1; }
+// A snapshot = header + the raw state slab.  The header pins what the slab's layout depends on, so that a blob taken
+// from a different configuration / order capacity / candle table length / library version is refused instead of being
+// reinterpreted.
+struct FxStateHeader {
+  uint32_t magic, abi, config_bytes, order_capacity;
+  uint64_t slab_bytes, config_hash;
+  int64_t table_rows[FXENV_MAX_PAIRS];
+};
+
+static FxStateHeader state_header(const FxEnv* env) {
+  FxStateHeader h;
+  memset(&h, 0, sizeof h);
+  h.magic = 0x32535846u;  // "FXS2"
+  h.abi = FXENV_ABI_VERSION;
+  h.config_bytes = (uint32_t)sizeof(FxConfig);
+  h.order_capacity = (uint32_t)env->P.cap;
+  h.slab_bytes = env->slab_bytes;
+  uint64_t x = 1469598103934665603ull;  // FNV-1a over the resolved config
+  const unsigned char* b = reinterpret_cast<const unsigned char*>(&env->P.cfg);
+  for (size_t i = 0; i < sizeof(FxConfig); i++) { x ^= b[i]; x *= 1099511628211ull; }
+  h.config_hash = x;
+  for (int p = 0; p < FXENV_MAX_PAIRS; p++) h.table_rows[p] = env->P.pair[p].T;
+  return h;
+}
+
+int64_t fxenv_state_bytes(const FxEnv* env) { return env ? (int64_t)(sizeof(FxStateHeader) + env->slab_bytes) : -1; }
 
 int fxenv_get_state(FxEnv* env, void* buf_host, int64_t nbytes) {
   if (!env || !buf_host) return FXENV_E_INVALID;
-  if (nbytes != (int64_t)env->slab_bytes) return fail(env, FXENV_E_INVALID, "state buffer size mismatch");
+  if (nbytes != fxenv_state_bytes(env)) return fail(env, FXENV_E_INVALID, "state buffer size mismatch");
   DeviceGuard g(env->device);
   FX_CUDA(env, cudaDeviceSynchronize());
-  FX_CUDA(env, cudaMemcpy(buf_host, env->slab, env->slab_bytes, cudaMemcpyDeviceToHost));
+  const FxStateHeader h = state_header(env);
+  memcpy(buf_host, &h, sizeof h);
+  FX_CUDA(env, cudaMemcpy(static_cast<char*>(buf_host) + sizeof h, env->slab, env->slab_bytes, cudaMemcpyDeviceToHost));
   return FXENV_OK;
 }
 
 int fxenv_set_state(FxEnv* env, const void* buf_host, int64_t nbytes) {
   if (!env || !buf_host) return FXENV_E_INVALID;
-  if (nbytes != (int64_t)env->slab_bytes) return fail(env, FXENV_E_INVALID, "state buffer size mismatch");
+  if (nbytes != fxenv_state_bytes(env)) return fail(env, FXENV_E_INVALID, "state buffer size mismatch");
+  FxStateHeader got;
+  memcpy(&got, buf_host, sizeof got);
+  const FxStateHeader want = state_header(env);
+  if (got.magic != want.magic || got.abi != want.abi) return fail(env, FXENV_E_INVALID, "not a state blob of this library version");
+  if (memcmp(&got, &want, sizeof got) != 0)
+    return fail(env, FXENV_E_INVALID, "state blob was taken from a different configuration (config / order capacity / candle tables differ)");
   DeviceGuard g(env->device);
   FX_CUDA(env, cudaDeviceSynchronize());
-  FX_CUDA(env, cudaMemcpy(env->slab, buf_host, env->slab_bytes, cudaMemcpyHostToDevice));
+  FX_CUDA(env, cudaMemcpy(env->slab, static_cast<const char*>(buf_host) + sizeof got, env->slab_bytes, cudaMemcpyHostToDevice));
   env->was_reset = true;
   env->first_reset = false;
   return FXENV_OK;

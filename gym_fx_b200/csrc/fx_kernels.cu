@@ -545,8 +545,12 @@ __device__ __forceinline__ void fx_step_env(const FxKernelParams& P, const void*
   double* __restrict__ gsz = st.o_sz + obase;
   uint32_t pm0 = gmeta[lane];
   double pp0 = gp0[lane], pp1 = gp1[lane], psz = gsz[lane];
+#ifndef FX_NO_RUN_STATS
   double rsv = (lane < FX_RS_N) ? st.rstats[(int64_t)env * FX_RS_N + lane] : 0.0;  // DrawDown / TradeAnalyzer / SQN state
   const FxRunStatsWarp rs{rsv, lane};
+#else   // A/B timing builds only
+  const FxRunStatsNone rs;
+#endif
 
 #ifdef FXENV_ENABLE_TIMING
   if (tstamp) {  // keep two consecutive steps: slot = parity of the (pre-step) cursor
@@ -743,10 +747,12 @@ __device__ __forceinline__ void fx_step_env(const FxKernelParams& P, const void*
       fx_mark_to_market(c, e, b.c);
       // DrawDown analyzer: one notify_fund + next per bar.  With no position and no execution the value is the one of
       // the previous bar and nothing can change.
+#ifndef FX_NO_RUN_STATS
       if (any_fill || e.psize != 0.0) {
         fx_rs_drawdown(rs, e.value);
         if (lane < FX_RS_N) st.rstats[(int64_t)env * FX_RS_N + lane] = rsv;
       }
+#endif
     }
     FX_STAMP(5);  // broker pass done, marked to market
     // candle of the next call (lanes 0..4): requested now, stored at the end of the env-step
@@ -957,14 +963,14 @@ fx_rollout_kernel(const __grid_constant__ FxKernelParams P, const char* __restri
       if (lane == 0) { while ((unsigned)fx_ld_acquire(P.seq + env) != seq_base + k) __nanosleep(32); }
       __syncwarp();
     }
-#ifdef FXENV_ENABLE_TIMING
+#if defined(FXENV_ENABLE_TIMING) || defined(FXENV_ENABLE_TIMELINE)
     if (P.timeline && lane == 0) { long long g__; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g__)); P.timeline[((size_t)k * N + env) * 2] = g__; }
 #endif
     fx_step_env<STRAT, REWARD, FAST5, false>(P, actions, obs, reward, nullptr, terminated, (int)env, lane, ws, phase, k * N,
                                       (k % (unsigned)obs_slots) * N);
     __syncwarp();
     if (lane == 0) fx_st_release(P.seq + env, (int)(seq_base + k + 1u));
-#ifdef FXENV_ENABLE_TIMING
+#if defined(FXENV_ENABLE_TIMING) || defined(FXENV_ENABLE_TIMELINE)
     if (P.timeline && lane == 0) { long long g__; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g__)); P.timeline[((size_t)k * N + env) * 2 + 1] = g__; }
 #endif
     g = __shfl_sync(FX_FULL, g_next, 0);

@@ -266,6 +266,15 @@ def test_step_many_graph_and_step_host_match_step(cfg2_full):
     a_env.set_state(blob)
     for k in range(3):
         assert torch.equal(a_env.step(acts[k])[1], ref[k])
+    # a blob whose header does not describe THIS env (other config hash / capacity / size) is refused, not reinterpreted
+    from gym_fx_b200._native import FxEnvError
+    bad = bytearray(blob); bad[24] ^= 0x5A
+    with pytest.raises(FxEnvError, match="different configuration"):
+        a_env.set_state(bytes(bad))
+    with pytest.raises(FxEnvError, match="size mismatch"):
+        a_env.set_state(blob[:-8])
+    with pytest.raises(FxEnvError, match="library version"):
+        a_env.set_state(b"\0" * len(blob))
     assert a_env.launch_count() >= K
     for e in (a_env, b_env, c_env):
         e.close()

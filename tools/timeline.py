@@ -33,7 +33,10 @@ t0 = tl[:, :, 0].min()
 st, en = (tl[:, :, 0] - t0) / 1e3, (tl[:, :, 1] - t0) / 1e3   # us
 print(f"first ticket start 0, last ticket end {en.max():.1f} us; env-step duration mean {np.mean(en-st):.2f} p50 {np.median(en-st):.2f} p99 {np.percentile(en-st,99):.2f} max {np.max(en-st):.2f} us")
 print(" step | first start  median start  last start | median end  last end | mean dur | gap to dep (start - end of same env's previous step): mean  p99")
-for k in range(K):
+show = range(K) if K <= 64 else sorted(set(list(range(0, 8)) + list(range(8, K, max(1, K // 48))) + [K - 1]))
+med = np.median(st, axis=1)
+print("step period (us, median start of step k+10 minus step k, /10):", " ".join(f"{(med[k+10]-med[k])/10:.1f}" for k in range(0, K - 10, max(1, K // 40))))
+for k in show:
     gap = st[k] - en[k - 1] if k else np.zeros(N)
     print(f"  {k:3d} | {st[k].min():9.1f} {np.median(st[k]):12.1f} {st[k].max():11.1f} | {np.median(en[k]):9.1f} {en[k].max():9.1f} | {np.mean(en[k]-st[k]):7.2f} | {gap.mean():8.2f} {np.percentile(gap,99):8.2f}")
 # busy warps over time
