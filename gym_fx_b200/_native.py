@@ -44,7 +44,7 @@ class FxInfoPtrs(C.Structure):
 
 RUN_STATS = 12  # FXENV_RUN_STATS
 RS = {"dd_maxvalue": 0, "dd_max_money": 1, "dd_max_pct": 2, "tr_pnl": 3, "tr_comm": 4, "tr_price": 5, "pnl_net": 6,
-      "sqn_mean": 7, "sqn_m2": 8, "opened": 9, "won": 10, "lost": 11}  # FXENV_RS_*
+      "pnl_sq": 7, "spare": 8, "opened": 9, "won": 10, "lost": 11}  # FXENV_RS_*
 
 
 INFO_DTYPES = {

@@ -189,6 +189,10 @@ int fxenv_create(const FxConfig* cfg, FxEnv** out) {
       cudaMemset(env->P.timeline, 0, nb);
     }
   }
+  env->P.any_binary = 0;
+  for (int i = 0; i < c.n_features; i++) if (c.feature_binary[i]) env->P.any_binary = 1;
+  if (c.preproc != FX_PREPROC_FEATURE_WINDOW) env->P.any_binary = 0;
+  env->P.lean = 0;  // decided in fxenv_load_candles (needs to know that the data are finite)
   ce = fx_configure_kernels(env->P);
   if (const char* rb = getenv("FXENV_ROLLOUT_BLOCKS"))  // timing experiments only: grid of the persistent launch
     if (atoi(rb) > 0 && atoi(rb) < env->P.resident_blocks) env->P.resident_blocks = atoi(rb);
@@ -297,6 +301,9 @@ int fxenv_load_candles(FxEnv* env, int pair_id, const double* candles_host, int6
   env->tame[pair_id] = tame;
   env->P.tame_data = 1;
   for (int p = 0; p < c.num_pairs; p++) if (env->loaded[p] && !env->tame[p]) env->P.tame_data = 0;
+  bool all_loaded = true;
+  for (int p = 0; p < c.num_pairs; p++) all_loaded = all_loaded && env->loaded[p];
+  env->P.lean = (all_loaded && !getenv("FXENV_NO_LEAN") && fx_config_is_lean(env->P)) ? 1 : 0;
   return FXENV_OK;
 }
 

@@ -130,21 +130,29 @@ FX_HD void fx_pseudo_execute(const FxConfig& c, double size, double price, doubl
 // app/bt_bridge.py:230-234) hold when the run ends; GymFxEnv.summary() -> metrics_plugins/default_metrics.py:48-60 reads
 // max.drawdown, max.moneydown, total.total, won.total, lost.total, pnl.net.average and sqn from them.  One record of
 // FX_RS_N doubles per env (the counters are stored as doubles: exact far beyond any run length).
+//
+// The per-fill part sits inside the hottest loop of the step (FIFO execution of the triggered orders), so it is kept to a
+// few operations: the open trade's average price is NOT tracked while it equals the position's average price (which
+// Position.update maintains with the very same recurrence) -- only when backtrader's Trade.update and Position.update
+// diverge (a trade opened with a size for which (size * price) / size != price, or an opening bit absorbed by rounding)
+// does FX_FLAG_TRADE_PRICE_OWN get set and the price kept in the record.  SQN uses the sums of pnl and pnl^2 of the
+// closed trades (no division per trade; evaluated at summary time, 1e-9 relative to backtrader's fsum-based value).
 enum {
   FX_RS_DD_MAXVALUE = 0,  // DrawDown._maxvalue: running peak of the broker value
   FX_RS_DD_MAX_MONEY,     // max.moneydown
   FX_RS_DD_MAX_PCT,       // max.drawdown (percent)
   FX_RS_TR_PNL,           // open Trade: gross pnl so far
   FX_RS_TR_COMM,          // open Trade: commission so far
-  FX_RS_TR_PRICE,         // open Trade: average price (Trade.update's own recurrence, not Position's)
+  FX_RS_TR_PRICE,         // open Trade: average price, valid only while FX_FLAG_TRADE_PRICE_OWN is set
   FX_RS_PNL_NET,          // TradeAnalyzer pnl.net.total = sum of pnlcomm over closed trades
-  FX_RS_SQN_MEAN,         // running mean / M2 (Welford) of pnlcomm over closed trades -> SQN
-  FX_RS_SQN_M2,
+  FX_RS_PNL_SQ,           // sum of pnlcomm^2 over closed trades (SQN)
+  FX_RS_SPARE,
   FX_RS_OPENED,           // TradeAnalyzer total.total (trades opened)
   FX_RS_WON,              // won.total  (pnlcomm >= 0)
   FX_RS_LOST,             // lost.total
   FX_RS_N
 };
+
 
 // Accessor the execution code is written against: the device keeps field i in lane i of one register (a single
 // coalesced load / store of the record per env-step), the host build and the reset path use a plain array.
@@ -152,11 +160,13 @@ struct FxRunStatsMem {
   double* v;
   FX_HD double get(int i) const { return v[i]; }
   FX_HD void set(int i, double x) const { v[i] = x; }
+  FX_HD void add(int i, double x) const { v[i] += x; }
 };
 
 struct FxRunStatsNone {  // statistics not tracked by this caller
   FX_HD double get(int) const { return 0.0; }
   FX_HD void set(int, double) const {}
+  FX_HD void add(int, double) const {}
 };
 
 template <class RS> struct FxRsOn { static const bool value = true; };
@@ -179,41 +189,52 @@ FX_HD void fx_rs_drawdown(const RS& rs, double value) {
 
 // Strategy._addnotification -> Trade.update for the two bits of one execution (closing part first, then the opening
 // part), and the analyzers' notify_trade when the trade closes / opens  [backtrader strategy.py, trade.py,
-// analyzers/tradeanalyzer.py, analyzers/sqn.py, restated].  `oldsize` = position size before the execution.
+// analyzers/tradeanalyzer.py, analyzers/sqn.py, restated].  oldsize / pprice_orig: the position before the execution,
+// pprice_new: its average price after; pnl = (-closed) * (price - pprice_orig) as computed by _execute.
 template <class RS>
-FX_HD void fx_rs_trade(const RS& rs, double oldsize, double closed, double opened, double price, double closedcomm,
-                       double openedcomm, int32_t closed_trades_after) {
-  double tprice = rs.get(FX_RS_TR_PRICE), tpnl = rs.get(FX_RS_TR_PNL), tcomm = rs.get(FX_RS_TR_COMM);
+FX_HD void fx_rs_trade(const RS& rs, uint32_t& flags, double oldsize, double closed, double opened, double price,
+                       double pnl, double pprice_orig, double pprice_new, double closedcomm, double openedcomm, bool has_comm) {
+  const bool own = (flags & FX_FLAG_TRADE_PRICE_OWN) != 0u;
   if (closed != 0.0) {
-    tcomm += closedcomm;
-    tpnl += (-closed) * (price - tprice);  // comminfo.profitandloss(-size, trade.price, price)
+    if (has_comm) rs.add(FX_RS_TR_COMM, closedcomm);
+    // comminfo.profitandloss(-size, trade.price, price); trade.price == position price unless flagged
+    rs.add(FX_RS_TR_PNL, own ? (-closed) * (price - rs.get(FX_RS_TR_PRICE)) : pnl);
     if (oldsize + closed == 0.0) {         // trade.isclosed
-      const double pnlcomm = tpnl - tcomm;
-      if (pnlcomm >= 0.0) rs.set(FX_RS_WON, rs.get(FX_RS_WON) + 1.0);
-      else rs.set(FX_RS_LOST, rs.get(FX_RS_LOST) + 1.0);
-      rs.set(FX_RS_PNL_NET, rs.get(FX_RS_PNL_NET) + pnlcomm);
-      double mean = rs.get(FX_RS_SQN_MEAN), m2 = rs.get(FX_RS_SQN_M2);
-      const double d = pnlcomm - mean;
-      mean += d / (double)closed_trades_after;
-      m2 += d * (pnlcomm - mean);
-      rs.set(FX_RS_SQN_MEAN, mean); rs.set(FX_RS_SQN_M2, m2);
-      tpnl = 0.0; tcomm = 0.0; tprice = 0.0;  // the next opening bit starts a fresh Trade()
+      const double pnlcomm = rs.get(FX_RS_TR_PNL) - (has_comm ? rs.get(FX_RS_TR_COMM) : 0.0);
+      rs.add(pnlcomm >= 0.0 ? FX_RS_WON : FX_RS_LOST, 1.0);
+      rs.add(FX_RS_PNL_NET, pnlcomm);
+      rs.add(FX_RS_PNL_SQ, pnlcomm * pnlcomm);
+      rs.set(FX_RS_TR_PNL, 0.0);           // the next opening bit starts a fresh Trade()
+      if (has_comm) rs.set(FX_RS_TR_COMM, 0.0);
+      flags &= ~FX_FLAG_TRADE_PRICE_OWN;
     }
   }
   if (opened != 0.0) {
     const double tsize = oldsize + closed, nsize = tsize + opened;
-    tcomm += openedcomm;
-    // Trade.update decides by |size after| > |size before|: an opening bit too small to change the size (absorbed by
-    // rounding, e.g. the close() of a 1e-12 dust position executing after the position has flipped) books a pnl instead
-    if (fabs(nsize) > fabs(tsize)) tprice = (tsize * tprice + opened * price) / nsize;
-    else tpnl += (-opened) * (price - tprice);
-    if (tsize == 0.0) rs.set(FX_RS_OPENED, rs.get(FX_RS_OPENED) + 1.0);  // trade.justopened
+    if (has_comm) rs.add(FX_RS_TR_COMM, openedcomm);
+    if (tsize == 0.0) {                    // trade.justopened: price = (0 * 0 + size * price) / size
+      rs.add(FX_RS_OPENED, 1.0);
+      if (fabs(opened) != 1.0) {           // exact for unit sizes; otherwise it can be one ulp off the fill price
+        const double tp = (opened * price) / nsize;
+        if (tp != price) { rs.set(FX_RS_TR_PRICE, tp); flags |= FX_FLAG_TRADE_PRICE_OWN; }
+      }
+    } else if (fabs(nsize) > fabs(tsize)) {  // increased: the same recurrence as Position.update while the prices agree
+      if (flags & FX_FLAG_TRADE_PRICE_OWN) rs.set(FX_RS_TR_PRICE, (tsize * rs.get(FX_RS_TR_PRICE) + opened * price) / nsize);
+    } else {
+      // Trade.update decides by |size after| > |size before|: an opening bit too small to change the size (absorbed by
+      // rounding, e.g. the close() of a 1e-12 dust position executing after the position has flipped) books a pnl and
+      // leaves the trade's price alone, while Position.update re-averages: from here on the two prices differ
+      const double tp = (flags & FX_FLAG_TRADE_PRICE_OWN) ? rs.get(FX_RS_TR_PRICE) : pprice_orig;
+      rs.add(FX_RS_TR_PNL, (-opened) * (price - tp));
+      if (!(flags & FX_FLAG_TRADE_PRICE_OWN) && pprice_new != pprice_orig) { rs.set(FX_RS_TR_PRICE, pprice_orig); flags |= FX_FLAG_TRADE_PRICE_OWN; }
+    }
   }
-  rs.set(FX_RS_TR_PRICE, tprice); rs.set(FX_RS_TR_PNL, tpnl); rs.set(FX_RS_TR_COMM, tcomm);
 }
 
 // ---- BackBroker._execute, real form.  Returns true if the order ended in Margin (=> cancel its bracket group) --
-template <class RS>
+// PLAIN (compile time): commission == 0 and leverage == 1 -- the arithmetic that those values turn into identities
+// (x / 1.0, x - 0.0) is left out; every remaining operation and its order are unchanged.
+template <bool PLAIN, class RS>
 FX_HD bool fx_execute(const FxConfig& c, FxEnvRegs& e, double size, double price, const RS& rs) {
   const double pprice_orig = e.pprice, oldsize = e.psize;
   double ps = e.psize, pp = e.pprice, opened, closed;
@@ -224,10 +245,12 @@ FX_HD bool fx_execute(const FxConfig& c, FxEnvRegs& e, double size, double price
   if (closed != 0.0) {
     const double closedvalue = (-closed) * pprice_orig;
     double closecash = closedvalue;
-    if (closedvalue > 0.0 && c.leverage != 1.0) closecash /= c.leverage;
+    if (!PLAIN && closedvalue > 0.0 && c.leverage != 1.0) closecash /= c.leverage;
     cash += closecash + pnl * 1.0;
-    closedcomm = fabs(closed) * c.commission * price;
-    cash -= closedcomm;
+    if (!PLAIN) {
+      closedcomm = fabs(closed) * c.commission * price;
+      cash -= closedcomm;
+    }
     cash += 0.0;  // stock-like cashadjust
     e.cash = cash;
   }
@@ -235,10 +258,12 @@ FX_HD bool fx_execute(const FxConfig& c, FxEnvRegs& e, double size, double price
   if (opened != 0.0) {
     const double openedvalue = opened * price;
     double opencash = openedvalue;
-    if (openedvalue > 0.0 && c.leverage != 1.0) opencash /= c.leverage;
+    if (!PLAIN && openedvalue > 0.0 && c.leverage != 1.0) opencash /= c.leverage;
     cash -= opencash;
-    openedcomm = fabs(opened) * c.commission * price;
-    cash -= openedcomm;
+    if (!PLAIN) {
+      openedcomm = fabs(opened) * c.commission * price;
+      cash -= openedcomm;
+    }
     if (cash < 0.0) { opened = 0.0; openedcomm = 0.0; }
     else e.cash = cash;
   }
@@ -250,9 +275,11 @@ FX_HD bool fx_execute(const FxConfig& c, FxEnvRegs& e, double size, double price
     // Trade bookkeeping (strategy._addnotification): a trade closes when the closing part of the execution
     // brings the position to exactly 0 -> BTBridgeStrategy.notify_trade (app/bt_bridge.py:115-117)
     if (closed != 0.0 && oldsize + closed == 0.0) e.trades += 1;
-    if (FxRsOn<RS>::value) fx_rs_trade(rs, oldsize, closed, opened, price, closedcomm, openedcomm, e.trades);
+    if (FxRsOn<RS>::value)
+      fx_rs_trade(rs, e.flags, oldsize, closed, opened, price, pnl, pprice_orig, e.pprice, closedcomm, openedcomm,
+                  !PLAIN && c.commission != 0.0);
     // BTBridgeStrategy.notify_order counts commission of COMPLETED orders only (app/bt_bridge.py:109-113)
-    if (size - execsize == 0.0) {
+    if (!PLAIN && size - execsize == 0.0) {
       double ocomm = 0.0;
       ocomm += closedcomm + openedcomm;
       e.commission_paid += ocomm;
@@ -399,7 +426,7 @@ FX_HD void fx_exec_entry(const FxConfig& c, FxEnvRegs& e, FxOrderTab& t, int k, 
   if (!go) return;
   // Completed or Margin: either way the entry leaves the table.  A child that completes cancels its sibling, a child
   // or parent that goes Margin cancels its whole group -- for a PAIR both mean "the pair is gone".
-  const bool margin = fx_execute(c, e, t.sz[k], px, rs);
+  const bool margin = fx_execute<false>(c, e, t.sz[k], px, rs);
   fx_kill(t, k);
   if (kind == FXO_PARENT) {
     if (margin) fx_kill(t, k + 1);
@@ -408,11 +435,12 @@ FX_HD void fx_exec_entry(const FxConfig& c, FxEnvRegs& e, FxOrderTab& t, int k, 
 }
 
 // ---- BackBroker._get_value (shortcash valuation; the long side is un-levered) -------------------------------------
+template <bool PLAIN = false>
 FX_HD void fx_mark_to_market(const FxConfig& c, FxEnvRegs& e, double pclose) {
   double unl = 0.0;
   double dvalue = e.psize * pclose;
   const double dunreal = e.psize * (pclose - e.pprice) * 1.0;
-  if (dvalue > 0.0) { dvalue -= dunreal; unl += dvalue / c.leverage; unl += dunreal; }
+  if (dvalue > 0.0) { dvalue -= dunreal; unl += PLAIN ? dvalue : dvalue / c.leverage; unl += dunreal; }
   else unl += dvalue;
   e.value = e.cash + unl;
 }

@@ -126,22 +126,29 @@ __device__ __forceinline__ int32_t fx_total_bars(const FxConfig& c, int64_t T, i
   return (int32_t)tb;
 }
 
+// LEAN (compile time, see fx_config_is_lean): the BASELINE family of configurations -- discrete actions, no commission /
+// leverage / slippage, backtrader's next-bar child activation, feature_window preprocessor over the 5 OHLCV columns with
+// a rolling z-score, clipping, price window and agent state, finite data.  The specialised kernels leave out every branch
+// and constant-bank read those settings make dead; results are bit-identical to the general kernels.
+template <bool LEAN = false>
 __device__ __forceinline__ bool fx_uses_running_stats(const FxConfig& c) {
-  return c.preproc == FX_PREPROC_FEATURE_WINDOW && c.scaling != FX_SCALING_NONE;
+  return LEAN || (c.preproc == FX_PREPROC_FEATURE_WINDOW && c.scaling != FX_SCALING_NONE);
 }
 
 // z-score statistics of the history window ending at local row s-1, for lane f < F: {mean, 1/std}.
 // Full rolling window: the per-bar table computed at load time.  Otherwise (warm-up, expanding): the env's running
 // Welford state (wm, wm2 = the lane's feature, already including row s-1).  Returns false -> raw (unscaled) values.
+template <bool LEAN = false>
 __device__ __forceinline__ bool fx_scaling_active(const FxConfig& c, int s, int& hn) {
-  if (!fx_uses_running_stats(c)) return false;
+  if (!fx_uses_running_stats<LEAN>(c)) return false;
   hn = s;
-  if (c.scaling == FX_SCALING_ROLLING && hn > c.scaling_window) hn = c.scaling_window;
+  if ((LEAN || c.scaling == FX_SCALING_ROLLING) && hn > c.scaling_window) hn = c.scaling_window;
   return hn >= 2;
 }
 
+template <bool LEAN = false>
 __device__ __forceinline__ bool fx_stats_from_table(const FxConfig& c, const FxPairTable& tb, int hn) {
-  return c.scaling == FX_SCALING_ROLLING && hn == c.scaling_window && tb.stats != nullptr;
+  return (LEAN || (c.scaling == FX_SCALING_ROLLING && tb.stats != nullptr)) && hn == c.scaling_window;
 }
 
 __device__ __forceinline__ void fx_welford_to_stats(double wm, double wm2, int hn, double& m, double& r) {
@@ -307,14 +314,16 @@ __device__ __noinline__ void fx_emit_fast5_q(const FxKernelParams& P, int lane, 
   const int W = c.window_size;
   const float clipf = (float)c.feature_clip;
   if (lane < 30) {
-    const int j4 = (lane % 5) * 4;
+    const int l5 = lane % 5;
     double r[4], a[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-      const int f = (j4 + i) % 5;
-      const bool z = scale && !c.feature_binary[f];
-      r[i] = z ? sstat[2 * f + 1] : 1.0;
-      a[i] = z ? -(sstat[2 * f] * r[i]) : 0.0;
+      int f = i - l5;                      // (4 * l5 + i) % 5, with 4 = -1 (mod 5)
+      if (f < 0) f += 5;
+      const bool z = scale && (!P.any_binary || !c.feature_binary[f]);
+      const double2 mr = *reinterpret_cast<const double2*>(sstat + 2 * f);  // {mean, 1/std}
+      r[i] = z ? mr.y : 1.0;
+      a[i] = z ? -(mr.x * mr.y) : 0.0;
     }
     const int nq = (5 * W) >> 2;
     float4* __restrict__ o4 = reinterpret_cast<float4*>(out);
@@ -347,10 +356,15 @@ __device__ __noinline__ void fx_emit_fast5_q(const FxKernelParams& P, int lane, 
   }
 }
 
-template <bool FAST5, bool O16 = true>
+template <bool FAST5, bool O16 = true, bool LEAN = false>
 __device__ __forceinline__ void fx_emit_windows(const FxKernelParams& P, int lane, int s, bool scale,
                                                 const double* __restrict__ win, const double* sstat,
                                                 float* __restrict__ out, uint16_t* __restrict__ o16 = nullptr) {
+  if (LEAN) {  // window % 4 == 0, price window, clip > 0 and finite data are part of the LEAN contract
+    if (s >= P.cfg.window_size && (reinterpret_cast<uintptr_t>(out) & 15) == 0) fx_emit_fast5_q<true, true, O16>(P, lane, scale, win, sstat, out, o16);
+    else fx_emit_windows_t<true, true, true, false, O16>(P, lane, s, scale, win, sstat, out, o16);
+    return;
+  }
   if (FAST5 && s >= P.cfg.window_size && (P.cfg.window_size & 3) == 0 && P.cfg.include_price_window &&
       P.cfg.feature_clip > 0.0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
     if (P.tame_data) fx_emit_fast5_q<true, true, O16>(P, lane, scale, win, sstat, out, o16);
@@ -394,18 +408,19 @@ __device__ __forceinline__ int fx_scalar_offset(const FxConfig& c) {
 
 // the 4 agent scalars at the end of the row (one lane)
 // `last` = price_column of the last window row (local row bar_index - 1)
+template <bool LEAN = false>
 __device__ __forceinline__ void fx_write_scalars(const FxKernelParams& P, const FxEnvRegs& e, int32_t total_bars,
                                                  double last, float* __restrict__ out, uint16_t* __restrict__ o16 = nullptr) {
   const FxConfig& c = P.cfg;
-  const bool inc_agent = (c.preproc == FX_PREPROC_DEFAULT) || c.include_agent_state;
+  const bool inc_agent = LEAN || (c.preproc == FX_PREPROC_DEFAULT) || c.include_agent_state;
   if (!inc_agent) return;
-  const bool inc_price = (c.preproc == FX_PREPROC_DEFAULT) || c.include_price_window;
+  const bool inc_price = LEAN || (c.preproc == FX_PREPROC_DEFAULT) || c.include_price_window;
   double ref;
-  if (c.preproc == FX_PREPROC_DEFAULT) ref = last;       // default_preprocessor.py:63
-  else ref = inc_price ? (double)(float)last : e.price;  // feature_window_preprocessor.py:218-222
+  if (!LEAN && c.preproc == FX_PREPROC_DEFAULT) ref = last;  // default_preprocessor.py:63
+  else ref = inc_price ? (double)(float)last : e.price;     // feature_window_preprocessor.py:218-222
   float sc[4];
   fx_agent_scalars(c, e, total_bars, ref, P.inv_initial_cash, sc);
-  const int so = fx_scalar_offset(c);
+  const int so = LEAN ? 7 * c.window_size : fx_scalar_offset(c);
   float* o = out + so;
   o[0] = sc[0]; o[1] = sc[1]; o[2] = sc[2]; o[3] = sc[3];
   fx_st16(o16, so, sc[0]); fx_st16(o16, so + 1, sc[1]); fx_st16(o16, so + 2, sc[2]); fx_st16(o16, so + 3, sc[3]);
@@ -469,6 +484,7 @@ struct FxRunStatsWarp {
   int lane;
   __device__ __forceinline__ double get(int i) const { return __shfl_sync(FX_FULL, v, i); }
   __device__ __forceinline__ void set(int i, double x) const { if (lane == i) v = x; }
+  __device__ __forceinline__ void add(int i, double x) const { if (lane == i) v += x; }  // no broadcast needed
 };
 
 // ---- the fused step --------------------------------------------------------------------------------------------
@@ -484,7 +500,7 @@ __device__ __forceinline__ uint32_t fx_apply_op(uint32_t m, uint32_t op) {
 }
 
 // One env-step of one env by one warp (everything between the cross-kernel dependency wait and the release).
-template <int STRAT, int REWARD, bool FAST5, bool O16>
+template <int STRAT, int REWARD, bool FAST5, bool O16, bool LEAN>
 __device__ __forceinline__ void fx_step_env(const FxKernelParams& P, const void* __restrict__ actions, float* __restrict__ obs,
                                             float* __restrict__ reward, double* __restrict__ reward64,
                                             uint8_t* __restrict__ terminated, const int env, const int lane, const WarpSmem& ws,
@@ -531,7 +547,7 @@ __device__ __forceinline__ void fx_step_env(const FxKernelParams& P, const void*
   e.value = e.equity;
   int action_raw_i = 0;
   float action_raw_f = 0.0f;
-  if (c.action_mode == FX_ACTION_CONTINUOUS) action_raw_f = reinterpret_cast<const float*>(actions)[FX_OUT_IDX()];
+  if (!LEAN && c.action_mode == FX_ACTION_CONTINUOUS) action_raw_f = reinterpret_cast<const float*>(actions)[FX_OUT_IDX()];
   else action_raw_i = reinterpret_cast<const int32_t*>(actions)[FX_OUT_IDX()];
   // the candle this call works on was saved by the previous call (FxDeviceState::nbar), and the first 32 orders of
   // the table sit at an address that only depends on the env: both travel in this same round trip
@@ -567,7 +583,7 @@ __device__ __forceinline__ void fx_step_env(const FxKernelParams& P, const void*
     if (c.auto_reset) {
       total_bars = fx_total_bars(c, tb.T, start);
       fx_reset_regs(c, e, tb.candles[start * (int64_t)C + 3]);
-      if (fx_uses_running_stats(c) && lane < c.n_features) {
+      if (fx_uses_running_stats<LEAN>(c) && lane < c.n_features) {
         const int64_t wi = ((int64_t)env * FXENV_MAX_FEATURES + lane) * 2;
         st.welford[wi] = tb.candles[start * (int64_t)C + c.feature_cols[lane]];
         st.welford[wi + 1] = 0.0;
@@ -588,7 +604,7 @@ __device__ __forceinline__ void fx_step_env(const FxKernelParams& P, const void*
       reward[FX_OUT_IDX()] = 0.0f;
       if (reward64) reward64[FX_OUT_IDX()] = 0.0;
       terminated[FX_OUT_IDX()] = c.auto_reset ? 0 : 1;
-      fx_write_scalars(P, e, total_bars, tb.candles[(start + e.bar_index - 1) * (int64_t)C + c.price_col], FX_OBS_ROW(), FX_OBS_ROW16());
+      fx_write_scalars<LEAN>(P, e, total_bars, tb.candles[(start + e.bar_index - 1) * (int64_t)C + c.price_col], FX_OBS_ROW(), FX_OBS_ROW16());
     }
     {
       const int s = e.bar_index;
@@ -598,7 +614,7 @@ __device__ __forceinline__ void fx_step_env(const FxKernelParams& P, const void*
       const int shift = fx_window_issue(tb, C, start, left, s - left, lane, ws);
       const bool scale = fx_prepare_stats(P, tb, env, lane, s, start, ws.stat);
       fx_window_wait(ws, phase);
-      fx_emit_windows<FAST5, O16>(P, lane, s, scale, ws.win + shift, ws.stat, FX_OBS_ROW(), FX_OBS_ROW16());
+      fx_emit_windows<FAST5, O16, LEAN>(P, lane, s, scale, ws.win + shift, ws.stat, FX_OBS_ROW(), FX_OBS_ROW16());
     }
     return;
   }
@@ -613,16 +629,16 @@ __device__ __forceinline__ void fx_step_env(const FxKernelParams& P, const void*
   // ---- the broker can start right away (candle + first 32 orders arrived with the state); what only the observation
   //      needs -- the candle window and the bar's z-score statistics -- is fetched by TMA bulk copies into shared
   //      memory while the broker runs, without occupying registers
-  const int dbg = P.debug;
+  const int dbg = LEAN ? 0 : P.debug;
   const int s_obs = t + 1;  // bar_index after this step
   const double* __restrict__ row = tb.candles + (start + t) * (int64_t)C;
   FxBar b;
   b.o = nb_oh.x; b.h = nb_oh.y; b.l = nb_lc.x; b.c = nb_lc.y;
   const double last_price = nb_price;
   int hn = 0;
-  const bool scale = fx_scaling_active(c, s_obs, hn);
-  const bool table_stats = scale && fx_stats_from_table(c, tb, hn);
-  const bool welford_live = advance && fx_uses_running_stats(c) && (c.scaling == FX_SCALING_EXPANDING || t + 1 <= c.scaling_window);
+  const bool scale = fx_scaling_active<LEAN>(c, s_obs, hn);
+  const bool table_stats = scale && fx_stats_from_table<LEAN>(c, tb, hn);
+  const bool welford_live = advance && fx_uses_running_stats<LEAN>(c) && ((!LEAN && c.scaling == FX_SCALING_EXPANDING) || t + 1 <= c.scaling_window);
 
   int win_left = s_obs - c.window_size;
   if (win_left < 0) win_left = 0;
@@ -657,7 +673,7 @@ __device__ __forceinline__ void fx_step_env(const FxKernelParams& P, const void*
     __syncwarp();                                                                                          \
     if (!(dbg & 1)) {                                                                                      \
       fx_window_wait(ws, phase);                                                                           \
-      fx_emit_windows<FAST5, O16>(P, lane, s_obs, scale, ws.win + win_shift, ws.stat, FX_OBS_ROW(), FX_OBS_ROW16()); \
+      fx_emit_windows<FAST5, O16, LEAN>(P, lane, s_obs, scale, ws.win + win_shift, ws.stat, FX_OBS_ROW(), FX_OBS_ROW16()); \
     }                                                                                                      \
   } while (0)
 
@@ -708,7 +724,7 @@ __device__ __forceinline__ void fx_step_env(const FxKernelParams& P, const void*
           }
           carry = 0u;
           double px_lane = 0.0;  // execution price of this lane's entry, should it trade on this bar
-          const bool hit = fx_entry_fill(c.slippage_perc, m, p0, p1, b, px_lane);
+          const bool hit = fx_entry_fill(LEAN ? 0.0 : c.slippage_perc, m, p0, p1, b, px_lane);
           uint32_t hm = __ballot_sync(FX_FULL, valid && !(m & FXO_DEAD) && hit);
           while (hm) {
             const int l = __ffs(hm) - 1;
@@ -718,14 +734,18 @@ __device__ __forceinline__ void fx_step_env(const FxKernelParams& P, const void*
             const uint32_t kind = bm & FXO_KIND_MASK;
             if (kind == FXO_PAIR && !(bm & FXO_ACTIVE)) continue;
             // Completed or Margin: either way the entry leaves the table (a PAIR: sibling / group cancelled)
-            const bool margin = fx_execute(c, e, __shfl_sync(FX_FULL, sz, l), __shfl_sync(FX_FULL, px_lane, l), rs);
+#ifdef FX_RS_NO_TRADE   // A/B timing builds only
+            const bool margin = fx_execute<LEAN>(c, e, __shfl_sync(FX_FULL, sz, l), __shfl_sync(FX_FULL, px_lane, l), FxRunStatsNone());
+#else
+            const bool margin = fx_execute<LEAN>(c, e, __shfl_sync(FX_FULL, sz, l), __shfl_sync(FX_FULL, px_lane, l), rs);
+#endif
             any_fill = true;
 #ifdef FXENV_ENABLE_TIMING
             n_fills++;
 #endif
             if (lane == l) m |= FXO_DEAD;
             if (kind == FXO_PARENT) {
-              const uint32_t op = margin ? FX_OP_KILL : (c.children_same_bar ? FX_OP_ACTIVATE : FX_OP_ACTIVATE_NEXT);
+              const uint32_t op = margin ? FX_OP_KILL : ((!LEAN && c.children_same_bar) ? FX_OP_ACTIVATE : FX_OP_ACTIVATE_NEXT);
               if (l < 31) { if (lane == l + 1) m = fx_apply_op(m, op); }
               else carry = op;
             }
@@ -744,13 +764,24 @@ __device__ __forceinline__ void fx_step_env(const FxKernelParams& P, const void*
         if (tstamp && lane == 0) tstamp[4] = ((long long)n << 32) | (long long)n_fills;  // debug: table size, fills
 #endif
       }
-      fx_mark_to_market(c, e, b.c);
+      fx_mark_to_market<LEAN>(c, e, b.c);
       // DrawDown analyzer: one notify_fund + next per bar.  With no position and no execution the value is the one of
       // the previous bar and nothing can change.
 #ifndef FX_NO_RUN_STATS
       if (any_fill || e.psize != 0.0) {
-        fx_rs_drawdown(rs, e.value);
-        if (lane < FX_RS_N) st.rstats[(int64_t)env * FX_RS_N + lane] = rsv;
+        // fx_rs_drawdown in the lane layout: ONE broadcast (the peak), then lanes 0 / 1 / 2 each test their own field;
+        // the percent needs its division only when it can set a new maximum.  The record goes back to memory only when
+        // something in it changed (an execution, a new peak, a new maximum drawdown).
+        const double peak0 = __shfl_sync(FX_FULL, rsv, FX_RS_DD_MAXVALUE);
+        const double peak = e.value > peak0 ? e.value : peak0;
+        const double md = peak - e.value;
+        double cand = (lane == FX_RS_DD_MAXVALUE) ? peak : md;
+        const bool pct_may = (lane == FX_RS_DD_MAX_PCT) && (100.0 * md > rsv * peak * 0.999999);
+        if (__any_sync(FX_FULL, pct_may)) { if (lane == FX_RS_DD_MAX_PCT) cand = pct_may ? 100.0 * md / peak : 0.0; }
+        else if (lane == FX_RS_DD_MAX_PCT) cand = 0.0;
+        const bool up = (lane <= FX_RS_DD_MAX_PCT) && (cand > rsv);
+        if (up) rsv = cand;
+        if (any_fill || __any_sync(FX_FULL, up)) { if (lane < FX_RS_N) st.rstats[(int64_t)env * FX_RS_N + lane] = rsv; }
       }
 #endif
     }
@@ -768,8 +799,8 @@ __device__ __forceinline__ void fx_step_env(const FxKernelParams& P, const void*
     int n_final = n_live, n_acc_new = n_live;
     double sub_need_new = 0.0;
     if (!exhausted) {
-      const int action = (c.action_mode == FX_ACTION_CONTINUOUS) ? fx_coerce_continuous(c, action_raw_f)
-                                                                 : fx_coerce_discrete(action_raw_i);
+      const int action = (!LEAN && c.action_mode == FX_ACTION_CONTINUOUS) ? fx_coerce_continuous(c, action_raw_f)
+                                                                           : fx_coerce_discrete(action_raw_i);
       double atr = 0.0;
       bool atr_ready = false;
       if (STRAT == FX_STRATEGY_ATR_SLTP && action != 0) {
@@ -801,7 +832,7 @@ __device__ __forceinline__ void fx_step_env(const FxKernelParams& P, const void*
       // bound is accumulated by fx_push and kept in the env state for the next step
       FxOrderTab tg;
       tg.meta = gmeta; tg.p0 = gp0; tg.p1 = gp1; tg.sz = gsz;
-      tg.n = n_live; tg.cap = P.cap; tg.dirty_from = n_live; tg.ndead = 0; tg.sub_need = 0.0; tg.bound_per = fx_bound_per(c);
+      tg.n = n_live; tg.cap = P.cap; tg.dirty_from = n_live; tg.ndead = 0; tg.sub_need = 0.0; tg.bound_per = LEAN ? 1.0 : fx_bound_per(c);
       fx_apply_action(c, STRAT, e, tg, action, b, pair, atr, atr_ready, has_min, minutes);
       n_final = tg.n;
       sub_need_new = tg.sub_need;
@@ -861,7 +892,7 @@ __device__ __forceinline__ void fx_step_env(const FxKernelParams& P, const void*
       reward[FX_OUT_IDX()] = (float)r;
       if (reward64) reward64[FX_OUT_IDX()] = r;
       terminated[FX_OUT_IDX()] = term ? 1 : 0;
-      fx_write_scalars(P, e, total_bars, last_price, FX_OBS_ROW(), FX_OBS_ROW16());
+      fx_write_scalars<LEAN>(P, e, total_bars, last_price, FX_OBS_ROW(), FX_OBS_ROW16());
     }
   } else {  // timing experiment only (FXENV_DEBUG & 2): cursor only
     if (lane == 0) { st.t[env] = t; st.flags[env] = flags; st.bar_index[env] = t + 1; reward[FX_OUT_IDX()] = 0.f; terminated[FX_OUT_IDX()] = 0; }
@@ -899,7 +930,7 @@ __device__ __forceinline__ void fx_st_release(int32_t* p, int v) {
 // the NEXT kernel of the stream / graph may be scheduled while this grid drains (its CTAs take SM slots as ours exit and
 // park at their own griddepcontrol.wait), which hides the launch gap between dependent steps.  Everything that touches
 // memory written by the previous kernel comes after the wait.
-template <int STRAT, int REWARD, bool FAST5>
+template <int STRAT, int REWARD, bool FAST5, bool LEAN>
 __global__ void __launch_bounds__(FX_WARPS * 32, FX_MIN_BLOCKS)
 fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict__ actions, float* __restrict__ obs,
                float* __restrict__ reward, double* __restrict__ reward64, uint8_t* __restrict__ terminated,
@@ -915,7 +946,7 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
   asm volatile("griddepcontrol.launch_dependents;");
   fx_window_init(lane, ws);  // mbarrier init + fence
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  fx_step_env<STRAT, REWARD, FAST5, true>(P, actions, obs, reward, reward64, terminated, env, lane, ws, 0u, 0u, 0u, obs16, stride16);
+  fx_step_env<STRAT, REWARD, FAST5, true, LEAN>(P, actions, obs, reward, reward64, terminated, env, lane, ws, 0u, 0u, 0u, obs16, stride16);
 }
 
 // ---- K steps in ONE launch (fxenv_step_many): persistent warps pull (step, env) tickets ----------------------------
@@ -930,7 +961,7 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
 #ifndef FX_ROLLOUT_MIN_BLOCKS
 #define FX_ROLLOUT_MIN_BLOCKS FX_MIN_BLOCKS
 #endif
-template <int STRAT, int REWARD, bool FAST5>
+template <int STRAT, int REWARD, bool FAST5, bool LEAN>
 __global__ void __launch_bounds__(FX_WARPS * 32, FX_ROLLOUT_MIN_BLOCKS)
 fx_rollout_kernel(const __grid_constant__ FxKernelParams P, const char* __restrict__ actions, float* __restrict__ obs,
                   const int obs_slots, float* __restrict__ reward, uint8_t* __restrict__ terminated, const int n_steps,
@@ -966,7 +997,7 @@ fx_rollout_kernel(const __grid_constant__ FxKernelParams P, const char* __restri
 #if defined(FXENV_ENABLE_TIMING) || defined(FXENV_ENABLE_TIMELINE)
     if (P.timeline && lane == 0) { long long g__; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g__)); P.timeline[((size_t)k * N + env) * 2] = g__; }
 #endif
-    fx_step_env<STRAT, REWARD, FAST5, false>(P, actions, obs, reward, nullptr, terminated, (int)env, lane, ws, phase, k * N,
+    fx_step_env<STRAT, REWARD, FAST5, false, LEAN>(P, actions, obs, reward, nullptr, terminated, (int)env, lane, ws, phase, k * N,
                                       (k % (unsigned)obs_slots) * N);
     __syncwarp();
     if (lane == 0) fx_st_release(P.seq + env, (int)(seq_base + k + 1u));
@@ -1063,42 +1094,53 @@ __global__ void fx_stats_kernel(FxConfig c, const double* __restrict__ candles, 
 }
 
 typedef void (*StepKernel)(const FxKernelParams, const void*, float*, float*, double*, uint8_t*, int, int, uint16_t*, int);
-
-template <int STRAT>
-StepKernel pick_reward(int reward, bool fast5) {
-  switch (reward) {
-    case FX_REWARD_PNL: return fast5 ? fx_step_kernel<STRAT, FX_REWARD_PNL, true> : fx_step_kernel<STRAT, FX_REWARD_PNL, false>;
-    case FX_REWARD_SHARPE: return fast5 ? fx_step_kernel<STRAT, FX_REWARD_SHARPE, true> : fx_step_kernel<STRAT, FX_REWARD_SHARPE, false>;
-    default: return fast5 ? fx_step_kernel<STRAT, FX_REWARD_DD, true> : fx_step_kernel<STRAT, FX_REWARD_DD, false>;
-  }
-}
-
-StepKernel pick_kernel(const FxKernelParams& P) {
-  const bool fast5 = P.fast_features == 5;
-  switch (P.cfg.strategy) {
-    case FX_STRATEGY_DEFAULT: return pick_reward<FX_STRATEGY_DEFAULT>(P.cfg.reward, fast5);
-    case FX_STRATEGY_FIXED_SLTP: return pick_reward<FX_STRATEGY_FIXED_SLTP>(P.cfg.reward, fast5);
-    default: return pick_reward<FX_STRATEGY_ATR_SLTP>(P.cfg.reward, fast5);
-  }
-}
-
 typedef void (*RolloutKernel)(const FxKernelParams, const char*, float*, int, float*, uint8_t*, int, unsigned, unsigned);
 
+// mode: 0 = general features, 1 = 5-feature fast path, 2 = LEAN (implies the 5-feature fast path)
+template <int STRAT, int REWARD>
+StepKernel pick_step_mode(int mode) {
+  if (mode == 2) return fx_step_kernel<STRAT, REWARD, true, true>;
+  return mode == 1 ? fx_step_kernel<STRAT, REWARD, true, false> : fx_step_kernel<STRAT, REWARD, false, false>;
+}
+template <int STRAT, int REWARD>
+RolloutKernel pick_rollout_mode(int mode) {
+  if (mode == 2) return fx_rollout_kernel<STRAT, REWARD, true, true>;
+  return mode == 1 ? fx_rollout_kernel<STRAT, REWARD, true, false> : fx_rollout_kernel<STRAT, REWARD, false, false>;
+}
 template <int STRAT>
-RolloutKernel pick_rollout_reward(int reward, bool fast5) {
+StepKernel pick_reward(int reward, int mode) {
   switch (reward) {
-    case FX_REWARD_PNL: return fast5 ? fx_rollout_kernel<STRAT, FX_REWARD_PNL, true> : fx_rollout_kernel<STRAT, FX_REWARD_PNL, false>;
-    case FX_REWARD_SHARPE: return fast5 ? fx_rollout_kernel<STRAT, FX_REWARD_SHARPE, true> : fx_rollout_kernel<STRAT, FX_REWARD_SHARPE, false>;
-    default: return fast5 ? fx_rollout_kernel<STRAT, FX_REWARD_DD, true> : fx_rollout_kernel<STRAT, FX_REWARD_DD, false>;
+    case FX_REWARD_PNL: return pick_step_mode<STRAT, FX_REWARD_PNL>(mode);
+    case FX_REWARD_SHARPE: return pick_step_mode<STRAT, FX_REWARD_SHARPE>(mode);
+    default: return pick_step_mode<STRAT, FX_REWARD_DD>(mode);
+  }
+}
+template <int STRAT>
+RolloutKernel pick_rollout_reward(int reward, int mode) {
+  switch (reward) {
+    case FX_REWARD_PNL: return pick_rollout_mode<STRAT, FX_REWARD_PNL>(mode);
+    case FX_REWARD_SHARPE: return pick_rollout_mode<STRAT, FX_REWARD_SHARPE>(mode);
+    default: return pick_rollout_mode<STRAT, FX_REWARD_DD>(mode);
   }
 }
 
-RolloutKernel pick_rollout(const FxKernelParams& P) {
-  const bool fast5 = P.fast_features == 5;
+int kernel_mode(const FxKernelParams& P, int lean) { return (lean && P.fast_features == 5) ? 2 : (P.fast_features == 5 ? 1 : 0); }
+
+StepKernel pick_kernel(const FxKernelParams& P, int lean = -1) {
+  const int mode = kernel_mode(P, lean < 0 ? P.lean : lean);
   switch (P.cfg.strategy) {
-    case FX_STRATEGY_DEFAULT: return pick_rollout_reward<FX_STRATEGY_DEFAULT>(P.cfg.reward, fast5);
-    case FX_STRATEGY_FIXED_SLTP: return pick_rollout_reward<FX_STRATEGY_FIXED_SLTP>(P.cfg.reward, fast5);
-    default: return pick_rollout_reward<FX_STRATEGY_ATR_SLTP>(P.cfg.reward, fast5);
+    case FX_STRATEGY_DEFAULT: return pick_reward<FX_STRATEGY_DEFAULT>(P.cfg.reward, mode);
+    case FX_STRATEGY_FIXED_SLTP: return pick_reward<FX_STRATEGY_FIXED_SLTP>(P.cfg.reward, mode);
+    default: return pick_reward<FX_STRATEGY_ATR_SLTP>(P.cfg.reward, mode);
+  }
+}
+
+RolloutKernel pick_rollout(const FxKernelParams& P, int lean = -1) {
+  const int mode = kernel_mode(P, lean < 0 ? P.lean : lean);
+  switch (P.cfg.strategy) {
+    case FX_STRATEGY_DEFAULT: return pick_rollout_reward<FX_STRATEGY_DEFAULT>(P.cfg.reward, mode);
+    case FX_STRATEGY_FIXED_SLTP: return pick_rollout_reward<FX_STRATEGY_FIXED_SLTP>(P.cfg.reward, mode);
+    default: return pick_rollout_reward<FX_STRATEGY_ATR_SLTP>(P.cfg.reward, mode);
   }
 }
 
@@ -1121,33 +1163,43 @@ cudaError_t fx_configure_kernels(FxKernelParams& P) {
   const size_t want = (size_t)FX_MIN_BLOCKS * (smem + 1024);
   int pct = (int)((want * 100 + 228 * 1024 - 1) / (228 * 1024));
   if (pct > 100) pct = 100;
-  {
-    cudaError_t e = cudaFuncSetAttribute(pick_kernel(P), cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  P.num_sms = sms > 0 ? sms : 1;
+  P.resident_blocks = 0;
+  // both the general and the LEAN instantiation: which one runs is only known once the candle tables are loaded
+  for (int lean = 0; lean <= (P.fast_features == 5 ? 1 : 0); lean++) {
+    cudaError_t e = cudaFuncSetAttribute(pick_kernel(P, lean), cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(pick_rollout(P, lean), cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     if (e != cudaSuccess) return e;
     if (smem > 48 * 1024) {
-      e = cudaFuncSetAttribute(pick_kernel(P), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      e = cudaFuncSetAttribute(pick_kernel(P, lean), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
-    }
-  }
-  {
-    cudaError_t e = cudaFuncSetAttribute(pick_rollout(P), cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-    if (e != cudaSuccess) return e;
-    if (smem > 48 * 1024) {
-      e = cudaFuncSetAttribute(pick_rollout(P), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      e = cudaFuncSetAttribute(pick_rollout(P, lean), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
     }
     // how many CTAs of the persistent rollout kernel the device holds at once (= its grid size)
-    int dev = 0, sms = 0, per_sm = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    P.num_sms = sms > 0 ? sms : 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_rollout(P), FX_WARPS * 32, smem);
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_rollout(P, lean), FX_WARPS * 32, smem);
     if (e != cudaSuccess) return e;
-    P.resident_blocks = sms * per_sm;
-    if (P.resident_blocks < 1) return cudaErrorInvalidConfiguration;
+    if (P.resident_blocks == 0 || sms * per_sm < P.resident_blocks) P.resident_blocks = sms * per_sm;
   }
+  if (P.resident_blocks < 1) return cudaErrorInvalidConfiguration;
   if (smem <= 48 * 1024) return cudaSuccess;
   return cudaFuncSetAttribute(fx_observe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)observe_smem_bytes(P));
+}
+
+// The LEAN contract of the specialised kernels (see fx_uses_running_stats): everything here is a property of the
+// resolved configuration except `tame_data`, which is known once every pair's candle table has been loaded.
+bool fx_config_is_lean(const FxKernelParams& P) {
+  const FxConfig& c = P.cfg;
+  if (P.fast_features != 5 || P.debug != 0 || !P.tame_data || P.any_binary) return false;
+  if (c.action_mode != FX_ACTION_DISCRETE || c.commission != 0.0 || c.leverage != 1.0 || c.slippage_perc != 0.0) return false;
+  if (c.children_same_bar || c.preproc != FX_PREPROC_FEATURE_WINDOW || c.scaling != FX_SCALING_ROLLING) return false;
+  if (!(c.feature_clip > 0.0) || !c.include_price_window || !c.include_agent_state || (c.window_size & 3) || c.price_col > 4) return false;
+  return true;
 }
 
 cudaError_t fx_launch_step(const FxKernelParams& P, const void* actions, float* obs, float* reward, double* reward64,

@@ -57,6 +57,8 @@ struct FxKernelParams {
   int32_t resident_blocks;  // CTAs of the persistent rollout kernel resident at once on this device (SMs x occupancy)
   int32_t tame_data;        // 1: every loaded table value is finite and |x| < 1e100 (no NaN can arise in a z-score)
   int32_t fast_features;    // 5: F == n_cols == 5 with identity columns (the [W][5] block is one contiguous span)
+  int32_t any_binary;       // 1: some feature column is a binary pass-through (feature_binary[])
+  int32_t lean;             // 1: the configuration qualifies for the specialised kernels (fx_config_is_lean)
   int32_t num_sms;          // SMs of the device (fx_rollout_kernel: CTA b is the (b / num_sms)-th CTA of its SM)
 };
 
@@ -84,6 +86,7 @@ cudaError_t fx_launch_observe(const FxKernelParams& P, float* obs, cudaStream_t 
                               int stride16 = 0);
 cudaError_t fx_launch_stats(const FxConfig& cfg, const double* candles, double* stats, int64_t T, cudaStream_t stream);
 cudaError_t fx_configure_kernels(FxKernelParams& P);
+bool fx_config_is_lean(const FxKernelParams& P);
 cudaError_t fx_launch_rollout(const FxKernelParams& P, const void* actions, float* obs, int obs_slots, float* reward,
                               uint8_t* terminated, int n_steps, unsigned seq_base, unsigned ticket_base, bool reset_words,
                               cudaStream_t stream);

@@ -236,9 +236,7 @@ class VecFxEnv:
         closed = i["trades"].double()
         nan = torch.full_like(closed, float("nan"))
         avg = torch.where(closed > 0, rs[:, R["pnl_net"]] / closed.clamp(min=1.0), nan)
-        sd = torch.sqrt(rs[:, R["sqn_m2"]] / closed.clamp(min=1.0))
-        sqn = torch.where(closed > 1, torch.where(sd > 0, torch.sqrt(closed) * rs[:, R["sqn_mean"]] / sd, nan),
-                          torch.zeros_like(closed))
+        sqn = self._sqn(rs[:, R["pnl_net"]], rs[:, R["pnl_sq"]], closed)
         return {
             "initial_cash": ic, "final_equity": eq, "total_return": ret,
             "max_drawdown_pct": rs[:, R["dd_max_pct"]], "max_drawdown_money": rs[:, R["dd_max_money"]],
@@ -253,6 +251,20 @@ class VecFxEnv:
             "order_overflow_envs": int((i["flags"] & 16).ne(0).sum()),
         }
 
+    @staticmethod
+    def _sqn(s1: torch.Tensor, s2: torch.Tensor, n: torch.Tensor) -> torch.Tensor:
+        """backtrader's SQN = sqrt(n) * mean / population std of the closed trades' net pnl, from their sum and sum of
+        squares; 0 for n <= 1 and NaN (the reference's None) when all trades had the same pnl (std == 0)."""
+        nn = n.clamp(min=1.0)
+        mean = s1 / nn
+        ex2 = s2 / nn
+        var = ex2 - mean * mean
+        degenerate = var <= 1e-12 * ex2          # rounding noise of the subtraction, not a variance
+        sd = torch.sqrt(var.clamp(min=0.0))
+        sqn = torch.sqrt(nn) * mean / torch.where(degenerate, torch.ones_like(sd), sd)
+        sqn = torch.where(degenerate, torch.full_like(sqn, float("nan")), sqn)
+        return torch.where(n > 1, sqn, torch.zeros_like(sqn))
+
     def analyzers(self, env: int = 0) -> Dict[str, Any]:
         """The analyzer results of ONE env in the shape of backtrader's get_analysis() dicts, as GymFxEnv.summary()
         hands them to the metrics plugin (app/env.py:258-265): trades / drawdown / sqn / sharpe / time_return."""
@@ -265,8 +277,9 @@ class VecFxEnv:
             trades.update(won={"total": int(rs[R["won"]])}, lost={"total": int(rs[R["lost"]])},
                           pnl={"net": {"total": float(rs[R["pnl_net"]]), "average": float(rs[R["pnl_net"]]) / closed}})
         if closed > 1:
-            sd = float(np.sqrt(rs[R["sqn_m2"]] / closed))
-            sqn = float(np.sqrt(closed) * rs[R["sqn_mean"]] / sd) if sd > 0 else None
+            v = float(self._sqn(torch.tensor([rs[R["pnl_net"]]], dtype=torch.float64), torch.tensor([rs[R["pnl_sq"]]], dtype=torch.float64),
+                                torch.tensor([float(closed)], dtype=torch.float64))[0])
+            sqn = None if v != v else v
         else:
             sqn = 0
         return {"trades": trades, "sqn": {"sqn": sqn, "trades": closed}, "sharpe": {}, "time_return": {},

@@ -61,6 +61,7 @@ enum { FX_SIZE_FX_UNITS = 0, FX_SIZE_NOTIONAL = 1 };
 #define FX_FLAG_EXHAUSTED 4u      /* data ran out (strategy.stop())       app/bt_bridge.py:152-155 */
 #define FX_FLAG_BROKE 8u          /* equity <= min_equity                 app/bt_bridge.py:203-204 */
 #define FX_FLAG_ORDER_OVERFLOW 16u/* order table full: an order was dropped (the reference is unbounded) */
+#define FX_FLAG_TRADE_PRICE_OWN 32u /* statistics bookkeeping: the open trade's average price differs from the position's */
 
 /*
  * The reference resolves one "dict of everything" at call time (app/config.py:1-45, plugin_params of every
@@ -156,9 +157,11 @@ enum {
   FXENV_RS_DD_MAXVALUE = 0, /* running peak of the broker value */
   FXENV_RS_DD_MAX_MONEY,    /* drawdown.max.moneydown */
   FXENV_RS_DD_MAX_PCT,      /* drawdown.max.drawdown (percent) */
-  FXENV_RS_TR_PNL, FXENV_RS_TR_COMM, FXENV_RS_TR_PRICE, /* the open trade */
+  FXENV_RS_TR_PNL, FXENV_RS_TR_COMM, FXENV_RS_TR_PRICE, /* the open trade (TR_PRICE valid only with FX_FLAG_TRADE_PRICE_OWN) */
   FXENV_RS_PNL_NET,         /* trades.pnl.net.total (average = / closed trades = FxInfoPtrs.trades) */
-  FXENV_RS_SQN_MEAN, FXENV_RS_SQN_M2, /* running mean / M2 of the closed trades' net pnl: sqn = sqrt(n) * mean / sqrt(M2 / n) */
+  FXENV_RS_PNL_SQ,          /* sum of squares of the closed trades' net pnl: with n = FxInfoPtrs.trades, mean = PNL_NET / n,
+                             * sqn = sqrt(n) * mean / sqrt(PNL_SQ / n - mean^2)  (n > 1) */
+  FXENV_RS_SPARE,
   FXENV_RS_OPENED,          /* trades.total.total */
   FXENV_RS_WON, FXENV_RS_LOST
 };

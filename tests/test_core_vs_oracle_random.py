@@ -70,7 +70,8 @@ def test_product_core_matches_oracle_on_random_configs(seed):
     if closed:
         assert rs[6] / closed == osum["avg_trade_pnl"], (seed, rs[6] / closed, osum["avg_trade_pnl"])
     if closed > 1 and osum["sqn"] == osum["sqn"]:
-        sqn = np.sqrt(closed) * rs[7] / np.sqrt(rs[8] / closed)
+        mean = rs[6] / closed
+        sqn = np.sqrt(closed) * mean / np.sqrt(rs[7] / closed - mean * mean)   # from the sums of pnl and pnl^2
         np.testing.assert_allclose(sqn, osum["sqn"], rtol=1e-9, err_msg=f"seed {seed}: sqn")
 
 
