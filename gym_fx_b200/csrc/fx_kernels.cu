@@ -151,10 +151,34 @@ __device__ __forceinline__ bool fx_stats_from_table(const FxConfig& c, const FxP
   return (LEAN || (c.scaling == FX_SCALING_ROLLING && tb.stats != nullptr)) && hn == c.scaling_window;
 }
 
+// 1 / n for a small positive integer: float reciprocal + two Newton steps in fp64 (relative error < 1e-15), ~8 instructions
+// instead of the ~35 of an IEEE fp64 division.  Only the observation statistics use it (tolerance 1e-5 on float32 values).
+__device__ __forceinline__ double fx_rcp_int(int n) {
+  const double x = (double)n;
+  double y = (double)__frcp_rn((float)n);
+  y = y * (2.0 - x * y);
+  y = y * (2.0 - x * y);
+  return y;
+}
+
+// {mean, 1 / std} of the running Welford state over hn rows; population std, std < 1e-8 -> 1 (feature_window_preprocessor.py
+// :110-116).  1/std by rsqrt + Newton (relative error < 1e-14) instead of division, square root and division.
 __device__ __forceinline__ void fx_welford_to_stats(double wm, double wm2, int hn, double& m, double& r) {
-  double sd = sqrt(wm2 / (double)hn);
-  if (sd < 1e-8) sd = 1.0;
-  m = wm; r = 1.0 / sd;
+  const double var = wm2 * fx_rcp_int(hn);
+  m = wm;
+  if (var < 1e-16) { r = 1.0; return; }                      // std < 1e-8 -> unscaled
+  if (!(var <= 1.0e300)) { r = 1.0 / sqrt(var); return; }    // inf / NaN in the data: IEEE semantics (NaN -> 0 downstream)
+  double y = (double)rsqrtf((float)var);
+  y = y * (1.5 - 0.5 * var * y * y);
+  y = y * (1.5 - 0.5 * var * y * y);
+  r = y;
+}
+
+// Welford update with the n-th row (n >= 1 after the update), 1/n by fx_rcp_int
+__device__ __forceinline__ void fx_welford_step(double& mean, double& m2, double x, int n) {
+  const double d = x - mean;
+  mean += d * fx_rcp_int(n);
+  m2 += d * (x - mean);
 }
 
 // self-contained version for the paths that are not latency critical (terminated envs, observe kernel)
@@ -306,20 +330,26 @@ __device__ __noinline__ void fx_emit_windows_t(const FxKernelParams& P, int lane
 // features are (4 * (lane % 5) + i) % 5 in every iteration, so their scale factors stay in registers, and a z-score is
 // ONE fp64 fma, x * (1/std) + (-mean / std) (the reference computes (x - mean) / std in fp64 and casts to float32; the
 // difference is far below half a float32 ulp).  prices | returns: a lane owns 4 consecutive rows.
-template <bool CLIP, bool TAME, bool O16>
+// PAD: the episode is younger than the window (s < W rows staged): output row w shows staged row max(0, w - pad), i.e. the
+// first row repeated `pad` times (feature_window_preprocessor.py:153-160,197-204) -- the first W steps of every episode.
+template <bool CLIP, bool TAME, bool O16, bool PAD>
 __device__ __noinline__ void fx_emit_fast5_q(const FxKernelParams& P, int lane, bool scale, const double* __restrict__ win,
-                                             const double* sstat, float* __restrict__ out, uint16_t* __restrict__ o16_) {
+                                             const double* sstat, float* __restrict__ out, uint16_t* __restrict__ o16_,
+                                             const int pad) {
   uint16_t* __restrict__ const o16 = O16 ? o16_ : nullptr;
   const FxConfig& c = P.cfg;
   const int W = c.window_size;
+  const int pad5 = 5 * pad;
   const float clipf = (float)c.feature_clip;
   if (lane < 30) {
     const int l5 = lane % 5;
     double r[4], a[4];
+    int fi[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
       int f = i - l5;                      // (4 * l5 + i) % 5, with 4 = -1 (mod 5)
       if (f < 0) f += 5;
+      fi[i] = f;
       const bool z = scale && (!P.any_binary || !c.feature_binary[f]);
       const double2 mr = *reinterpret_cast<const double2*>(sstat + 2 * f);  // {mean, 1/std}
       r[i] = z ? mr.y : 1.0;
@@ -329,7 +359,14 @@ __device__ __noinline__ void fx_emit_fast5_q(const FxKernelParams& P, int lane, 
     float4* __restrict__ o4 = reinterpret_cast<float4*>(out);
 #pragma unroll 1
     for (int q = lane; q < nq; q += 30) {
-      const double* __restrict__ x = win + 4 * q;  // the staged span may start on an odd double: 8-byte loads
+      double x[4];
+      if (PAD) {  // element j of the block comes from staged element j - 5 * pad, or from row 0 (same feature) in the pad
+#pragma unroll
+        for (int i = 0; i < 4; i++) { const int j = 4 * q + i - pad5; x[i] = win[j >= 0 ? j : fi[i]]; }
+      } else {
+        const double* __restrict__ xs = win + 4 * q;  // the staged span may start on an odd double: 8-byte loads
+        x[0] = xs[0]; x[1] = xs[1]; x[2] = xs[2]; x[3] = xs[3];
+      }
       float4 v;
       v.x = fx_finish_t<CLIP, TAME>((float)fma(x[0], r[0], a[0]), clipf);
       v.y = fx_finish_t<CLIP, TAME>((float)fma(x[1], r[1], a[1]), clipf);
@@ -343,9 +380,17 @@ __device__ __noinline__ void fx_emit_fast5_q(const FxKernelParams& P, int lane, 
   float* __restrict__ op = out + 5 * W;
 #pragma unroll 1
   for (int w0 = 4 * lane; w0 < W; w0 += 128) {
-    const double* __restrict__ pr = win + w0 * 5 + pc;
-    const double pm = (w0 > 0) ? pr[-5] : pr[0];
-    const double p0 = pr[0], p1 = pr[5], p2 = pr[10], p3 = pr[15];
+    double pm, p0, p1, p2, p3;
+    if (PAD) {
+      const int k = w0 - pad;  // staged row of output row w0 (negative inside the pad: row 0)
+      pm = win[(k - 1 > 0 ? k - 1 : 0) * 5 + pc];
+      p0 = win[(k > 0 ? k : 0) * 5 + pc]; p1 = win[(k + 1 > 0 ? k + 1 : 0) * 5 + pc];
+      p2 = win[(k + 2 > 0 ? k + 2 : 0) * 5 + pc]; p3 = win[(k + 3 > 0 ? k + 3 : 0) * 5 + pc];
+    } else {
+      const double* __restrict__ pr = win + w0 * 5 + pc;
+      pm = (w0 > 0) ? pr[-5] : pr[0];
+      p0 = pr[0]; p1 = pr[5]; p2 = pr[10]; p3 = pr[15];
+    }
     float4 pv, rv;
     pv.x = (float)p0; pv.y = (float)p1; pv.z = (float)p2; pv.w = (float)p3;
     rv.x = (w0 > 0) ? (float)(p0 - pm) : 0.0f; rv.y = (float)(p1 - p0); rv.z = (float)(p2 - p1); rv.w = (float)(p3 - p2);
@@ -360,15 +405,20 @@ template <bool FAST5, bool O16 = true, bool LEAN = false>
 __device__ __forceinline__ void fx_emit_windows(const FxKernelParams& P, int lane, int s, bool scale,
                                                 const double* __restrict__ win, const double* sstat,
                                                 float* __restrict__ out, uint16_t* __restrict__ o16 = nullptr) {
+  const int pad = P.cfg.window_size - s;  // > 0: the first rows of the window repeat the episode's first bar
   if (LEAN) {  // window % 4 == 0, price window, clip > 0 and finite data are part of the LEAN contract
-    if (s >= P.cfg.window_size && (reinterpret_cast<uintptr_t>(out) & 15) == 0) fx_emit_fast5_q<true, true, O16>(P, lane, scale, win, sstat, out, o16);
-    else fx_emit_windows_t<true, true, true, false, O16>(P, lane, s, scale, win, sstat, out, o16);
+    if ((reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+      if (pad <= 0) fx_emit_fast5_q<true, true, O16, false>(P, lane, scale, win, sstat, out, o16, 0);
+      else fx_emit_fast5_q<true, true, O16, true>(P, lane, scale, win, sstat, out, o16, pad);
+    } else {
+      fx_emit_windows_t<true, true, true, false, O16>(P, lane, s, scale, win, sstat, out, o16);
+    }
     return;
   }
-  if (FAST5 && s >= P.cfg.window_size && (P.cfg.window_size & 3) == 0 && P.cfg.include_price_window &&
-      P.cfg.feature_clip > 0.0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
-    if (P.tame_data) fx_emit_fast5_q<true, true, O16>(P, lane, scale, win, sstat, out, o16);
-    else fx_emit_fast5_q<true, false, O16>(P, lane, scale, win, sstat, out, o16);
+  if (FAST5 && (P.cfg.window_size & 3) == 0 && P.cfg.include_price_window && P.cfg.feature_clip > 0.0 && P.tame_data &&
+      (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    if (pad <= 0) fx_emit_fast5_q<true, true, O16, false>(P, lane, scale, win, sstat, out, o16, 0);
+    else fx_emit_fast5_q<true, true, O16, true>(P, lane, scale, win, sstat, out, o16, pad);
     return;
   }
   const bool lng = P.cfg.window_size >= 384;
@@ -661,7 +711,7 @@ __device__ __forceinline__ void fx_step_env(const FxKernelParams& P, const void*
       const int64_t wi = ((int64_t)env * FXENV_MAX_FEATURES + lane) * 2;                                   \
       double wf_m = st.welford[wi], wf_m2 = st.welford[wi + 1];                                            \
       if (welford_live) {                                                                                  \
-        fx_welford_add(wf_m, wf_m2, row[c.feature_cols[lane]], t + 1);                                     \
+        fx_welford_step(wf_m, wf_m2, row[c.feature_cols[lane]], t + 1);                                    \
         st.welford[wi] = wf_m; st.welford[wi + 1] = wf_m2;                                                 \
       }                                                                                                    \
       if (scale && !table_stats) {                                                                         \
