@@ -973,7 +973,11 @@ __device__ __forceinline__ int fx_ld_acquire(const int32_t* p) {
   return v;
 }
 __device__ __forceinline__ void fx_st_release(int32_t* p, int v) {
+#ifdef FX_UNSAFE_NO_FENCE  // TIMING EXPERIMENT ONLY (results are racy): what would a fence-free hand-over be worth?
+  asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+#else
   asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+#endif
 }
 
 // The single-step kernel: one warp per env, one env per CTA.  Launched with the programmatic-dependent-launch attribute:

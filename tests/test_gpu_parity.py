@@ -193,37 +193,46 @@ def test_full_size_shard_invariance_determinism_and_sampled_oracle(cfg2_full):
     starts = start_offsets(N, T, steps, 256)
     acts = np.random.default_rng(1234).integers(0, 3, (steps, N)).astype(np.int32)
 
+    samp = np.arange(0, N, 64)   # the envs whose observation is kept at EVERY step (a multiple of the shard stride)
+
     def run(sel):
+        """-> per step (obs of the kept envs, reward32, reward64, terminated) + final info.  The observation of every
+        env is compared every 40th step; of the kept envs (`samp`) at every step."""
         c2, _, _ = _mk(dict(window_size=128, **FW), dict(strategy="direct_fixed_sltp",
                        preprocessor="feature_window_preprocessor"), len(sel), T=T)
         g = GpuVec(c2, candles, minutes)
         g.reset(starts[sel])
-        outs = [g.step(acts[k, sel], want_obs=(k % 40 == 39 or k == steps - 1)) for k in range(steps)]
+        keep = np.nonzero(np.isin(sel, samp))[0]
+        outs, fulls = [], {}
+        for k in range(steps):
+            o = g.step(acts[k, sel], want_obs=True)
+            if k % 40 == 39 or k == steps - 1:
+                fulls[k] = o[0]
+            outs.append((o[0][keep].copy(), o[1], o[2], o[3]))
         inf = g.info()
         g.close()
-        return outs, inf
+        return outs, fulls, inf
 
-    full, finf = run(np.arange(N))
-    again, ainf = run(np.arange(N))
+    full, ffull, finf = run(np.arange(N))
+    again, afull, ainf = run(np.arange(N))
     sel = np.arange(0, N, 8)
-    shard, sinf = run(sel)
+    shard, sfull, sinf = run(sel)
     for k in range(steps):
-        for j in range(4):
-            if full[k][j] is None:
-                continue
+        assert np.array_equal(full[k][0], again[k][0]) and np.array_equal(full[k][0], shard[k][0]), f"kept-env obs at step {k}"
+        for j in range(1, 4):
             assert np.array_equal(full[k][j], again[k][j]), f"non-deterministic output {j} at step {k}"
             assert np.array_equal(full[k][j][sel], shard[k][j]), f"shard-dependent output {j} at step {k}"
+    for k in ffull:
+        assert np.array_equal(ffull[k], afull[k]) and np.array_equal(ffull[k][sel], sfull[k]), f"full obs at step {k}"
     for key in ("equity", "cash", "trades", "n_orders"):
         assert np.array_equal(finf[key][sel], sinf[key])
-    samp = np.arange(0, N, 64)
     c3, _, _ = _mk(dict(window_size=128, **FW), dict(strategy="direct_fixed_sltp",
                    preprocessor="feature_window_preprocessor"), len(samp), T=T)
     orc = OracleVec(c3, candles, minutes)
     orc.reset(starts[samp])
-    for k in range(steps):
+    for k in range(steps):   # the sampled envs against the oracle at EVERY step, observation included
         oo = orc.step(acts[k, samp])
-        go = tuple(None if x is None else x[samp] for x in full[k])
-        compare_step(f"full-size sample step {k}", (go[0], go[1], go[2], go[3]), oo if go[0] is not None else (None,) + oo[1:])
+        compare_step(f"full-size sample step {k}", (full[k][0], full[k][1][samp], full[k][2][samp], full[k][3][samp]), oo)
     oi = orc.info()
     assert np.array_equal(finf["equity"][samp], oi["equity"]) and np.array_equal(finf["trades"][samp], oi["trades"])
 
@@ -424,25 +433,26 @@ def test_full_size_other_baseline_shapes(case, N, pairs_kw):
         cfg, candles, minutes = _mk(cfgd, plugins, len(sel), T=T, order_capacity=256, **kw)
         env = VecFxEnv(cfg, candles, minutes)
         env.reset(torch.as_tensor(starts[sel]))
-        ring = torch.zeros((1, len(sel), env.obs_dim), dtype=torch.float32, device="cuda")
+        ring = torch.zeros((K, len(sel), env.obs_dim), dtype=torch.float32, device="cuda")   # one slot per step
         rews = torch.zeros((K, len(sel)), dtype=torch.float32, device="cuda")
         terms = torch.zeros((K, len(sel)), dtype=torch.uint8, device="cuda")
         env.step_many(torch.as_tensor(np.ascontiguousarray(actions[:, sel])).cuda(), ring, rews, terms)
         torch.cuda.synchronize()
-        out = (ring[0].cpu().numpy(), rews.cpu().numpy(), terms.cpu().numpy(),
+        out = ((ring[K - 1].cpu().numpy(), ring[:, :48].cpu().numpy()), rews.cpu().numpy(), terms.cpu().numpy(),
                {k: env.info()[k].cpu().numpy() for k in ("equity", "cash", "trades", "position", "bar_index", "flags")},
                env.step_many_engine(K))
         env.close()
         return out, (cfg, candles, minutes)
 
     allenv = np.arange(N)
-    (obs, rews, terms, inf, engine), _ = run(allenv, acts)
+    ((obs, obs_all_steps), rews, terms, inf, engine), _ = run(allenv, acts)
     assert engine == "graph" and not np.any(inf["flags"] & 16)
-    (obs2, rews2, terms2, inf2, _), _ = run(allenv, acts)
+    ((obs2, obs_all_steps2), rews2, terms2, inf2, _), _ = run(allenv, acts)
     assert np.array_equal(obs, obs2) and np.array_equal(rews, rews2) and np.array_equal(inf["equity"], inf2["equity"])
+    assert np.array_equal(obs_all_steps, obs_all_steps2)
     # same pair assignment needs the same (global id % pairs): take every 16th env (16 % 4 == 0)
     sel = allenv[::16]
-    (obs_s, rews_s, terms_s, inf_s, _), (cfg_s, candles, minutes) = run(sel, acts)
+    ((obs_s, _), rews_s, terms_s, inf_s, _), (cfg_s, candles, minutes) = run(sel, acts)
     if cfg_s.num_pairs > 1:
         assert np.all(sel % cfg_s.num_pairs == 0)   # all of them trade pair 0 in both runs only if ids line up
     if cfg_s.num_pairs == 1:
@@ -458,9 +468,10 @@ def test_full_size_other_baseline_shapes(case, N, pairs_kw):
         oo = orc.step(acts[k, samp])
         np.testing.assert_allclose(rews[k, samp], oo[1], rtol=1e-5, atol=1e-12, err_msg=f"{case} step {k}: reward")
         assert np.array_equal(terms[k, samp], oo[3])
+        np.testing.assert_allclose(obs_all_steps[k], oo[0], rtol=1e-5, atol=2e-6, err_msg=f"{case} step {k}: obs of the sampled envs")
     np.testing.assert_allclose(obs[samp], oo[0], rtol=1e-5, atol=2e-6, err_msg=f"{case}: last obs")
     oi = orc.info()
     assert np.array_equal(inf["equity"][samp], oi["equity"]) and np.array_equal(inf["trades"][samp], oi["trades"])
     # flat policy: equity untouched (tools/smoke_test.py:113-118 of the reference)
-    (_, rews_f, _, inf_f, _), _ = run(allenv, np.zeros_like(acts))
+    (_, rews_f, _, inf_f, _), _ = run(allenv, np.zeros_like(acts))  # noqa: the obs pair is unused here
     assert np.all(inf_f["equity"] == 10000.0) and np.all(inf_f["trades"] == 0) and np.all(rews_f[1:] == 0.0)
