@@ -574,6 +574,9 @@ struct FxPolicy {
   uint16_t* obs16[2] = {nullptr, nullptr};  // bf16 [num_envs][k_pad], double buffered
   int32_t* scratch_act = nullptr;      // bootstrap evaluation: action / logp are discarded
   float* scratch_logp = nullptr;
+  static constexpr int kGroups = 4;     // env groups of a rollout (see enqueue_rollout)
+  cudaStream_t side[kGroups - 1] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[kGroups - 1] = {};
   CUtensorMap map_obs[2], map_w1, map_w2;
   FxPolicyDev dev;
   bool has_weights = false;
@@ -606,22 +609,52 @@ int make_map(FxEnv* env, CUtensorMap* map, void* base, uint64_t rows, uint64_t c
   return FXENV_OK;
 }
 
+// The envs are independent, so a rollout is run as up to 4 env GROUPS, each its own chain
+//   policy(group, t) -> step(group, t) -> policy(group, t + 1) -> ...
+// on its own stream (forked from / joined into the caller's stream; inside a capture this becomes parallel branches of
+// the graph).  While one group's 128-row policy tiles occupy a few SMs, the other groups' env steps use the rest of the
+// device, and a group of <= 1024 envs steps in a single wave instead of the two of a 4096-env launch.
 cudaError_t enqueue_rollout(FxEnv* env, FxPolicy* pol, const FxRollout& io, cudaStream_t s) {
   const size_t N = (size_t)env->P.cfg.num_envs, D = (size_t)env->P.obs_dim;
   const int H = io.horizon, slots = io.obs_slots;
   cudaError_t e = fx_launch_observe(env->P, io.obs, s, pol->obs16[0], pol->k_pad);  // the current observation, both copies
   if (e != cudaSuccess) return e;
-  for (int t = 0; t < H; t++) {
-    e = fx_launch_policy(pol->map_obs[t & 1], pol->map_w1, pol->map_w2, pol->dev, (int)N, pol->k_pad,
-                         io.gumbel ? io.gumbel + (size_t)t * N * 3 : nullptr, io.seed, (unsigned)t, io.actions + (size_t)t * N,
-                         io.logp + (size_t)t * N, io.value + (size_t)t * N, s);
-    if (e != cudaSuccess) return e;
-    e = fx_launch_step(env->P, io.actions + (size_t)t * N, io.obs + (size_t)((t + 1) % slots) * N * D, io.reward + (size_t)t * N,
-                       nullptr, io.done + (size_t)t * N, s, 0, -1, pol->obs16[(t + 1) & 1], pol->k_pad);
+  int groups = (int)(N / 1024);
+  if (groups > FxPolicy::kGroups) groups = FxPolicy::kGroups;
+  if (groups < 1 || (env->P.debug & 64)) groups = 1;
+  const size_t per = ((N + groups - 1) / groups + FX_POLICY_TILE_M - 1) / FX_POLICY_TILE_M * FX_POLICY_TILE_M;
+  if (groups > 1) {
+    e = cudaEventRecord(pol->ev_fork, s);
     if (e != cudaSuccess) return e;
   }
-  return fx_launch_policy(pol->map_obs[H & 1], pol->map_w1, pol->map_w2, pol->dev, (int)N, pol->k_pad, nullptr, io.seed,
-                          (unsigned)H, pol->scratch_act, pol->scratch_logp, io.value + (size_t)H * N, s);
+  for (int g = 0; g < groups; g++) {
+    const size_t e0 = (size_t)g * per, e1 = (e0 + per < N) ? e0 + per : N;
+    if (e0 >= e1) break;
+    cudaStream_t sg = (g == 0) ? s : pol->side[g - 1];
+    if (g > 0) {
+      e = cudaStreamWaitEvent(sg, pol->ev_fork, 0);
+      if (e != cudaSuccess) return e;
+    }
+    for (int t = 0; t <= H; t++) {
+      const bool last = (t == H);  // the bootstrap evaluation: value only
+      e = fx_launch_policy(pol->map_obs[t & 1], pol->map_w1, pol->map_w2, pol->dev, (int)N, pol->k_pad,
+                           (!last && io.gumbel) ? io.gumbel + (size_t)t * N * 3 : nullptr, io.seed, (unsigned)t,
+                           last ? pol->scratch_act : io.actions + (size_t)t * N, last ? pol->scratch_logp : io.logp + (size_t)t * N,
+                           io.value + (size_t)t * N, sg, (int)e0, (int)e1);
+      if (e != cudaSuccess) return e;
+      if (last) break;
+      e = fx_launch_step(env->P, io.actions + (size_t)t * N, io.obs + (size_t)((t + 1) % slots) * N * D, io.reward + (size_t)t * N,
+                         nullptr, io.done + (size_t)t * N, sg, (int)e0, (int)e1, pol->obs16[(t + 1) & 1], pol->k_pad);
+      if (e != cudaSuccess) return e;
+    }
+    if (g > 0) {
+      e = cudaEventRecord(pol->ev_join[g - 1], sg);
+      if (e != cudaSuccess) return e;
+      e = cudaStreamWaitEvent(s, pol->ev_join[g - 1], 0);
+      if (e != cudaSuccess) return e;
+    }
+  }
+  return cudaSuccess;
 }
 
 }  // namespace
@@ -634,6 +667,9 @@ int fxenv_policy_destroy(FxPolicy* pol) {
   if (pol->cached.exec) cudaGraphExecDestroy(pol->cached.exec);
   cudaFree(pol->w1); cudaFree(pol->w2); cudaFree(pol->fparams); cudaFree(pol->obs16[0]); cudaFree(pol->obs16[1]);
   cudaFree(pol->scratch_act); cudaFree(pol->scratch_logp);
+  for (auto& st : pol->side) if (st) cudaStreamDestroy(st);
+  if (pol->ev_fork) cudaEventDestroy(pol->ev_fork);
+  for (auto& ev : pol->ev_join) if (ev) cudaEventDestroy(ev);
   delete pol;
   return FXENV_OK;
 }
@@ -665,7 +701,10 @@ int fxenv_policy_create(FxEnv* env, FxPolicy** out) {
   if (!rc) rc = make_map(env, &pol->map_w2, pol->w2, Hd, Hd, FX_POLICY_HIDDEN);
   if (rc) { fxenv_policy_destroy(pol); return rc; }
   cudaError_t ce = fx_policy_configure();
-  if (ce != cudaSuccess) { fxenv_policy_destroy(pol); return cuda_fail(env, ce, "fx_policy_configure"); }
+  for (auto& st : pol->side) if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+  if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&pol->ev_fork, cudaEventDisableTiming);
+  for (auto& ev : pol->ev_join) if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+  if (ce != cudaSuccess) { fxenv_policy_destroy(pol); return cuda_fail(env, ce, "fx_policy_configure / streams"); }
   *out = pol;
   return FXENV_OK;
 }

@@ -132,14 +132,14 @@ __global__ void __launch_bounds__(kThreads, 1)
 fx_policy_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_constant__ CUtensorMap map_w1,
                  const __grid_constant__ CUtensorMap map_w2, const FxPolicyDev pol, const int num_envs, const int k_blocks1,
                  const float* __restrict__ gumbel, const unsigned long long seed, const unsigned step,
-                 int32_t* __restrict__ action, float* __restrict__ logp, float* __restrict__ value) {
+                 int32_t* __restrict__ action, float* __restrict__ logp, float* __restrict__ value, const int env_begin) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   Barriers* bar = reinterpret_cast<Barriers*>(smem + kOffBar);
   float* head_w = reinterpret_cast<float*>(smem + kOffHeadW);
   float* bias = reinterpret_cast<float*>(smem + kOffBias);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * kTileM;
+  const int m0 = env_begin + blockIdx.x * kTileM;  // a launch covers the envs [env_begin, num_envs) (env groups of a rollout)
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_obs) : "memory");
@@ -321,9 +321,11 @@ cudaError_t fx_policy_configure() {
 
 cudaError_t fx_launch_policy(const CUtensorMap& map_obs, const CUtensorMap& map_w1, const CUtensorMap& map_w2,
                              const FxPolicyDev& pol, int num_envs, int k_pad, const float* gumbel, unsigned long long seed,
-                             unsigned step, int32_t* action, float* logp, float* value, cudaStream_t stream) {
+                             unsigned step, int32_t* action, float* logp, float* value, cudaStream_t stream, int env_begin,
+                             int env_end) {
+  if (env_end < 0) env_end = num_envs;
   cudaLaunchConfig_t lc = {};
-  lc.gridDim = dim3((num_envs + kTileM - 1) / kTileM);
+  lc.gridDim = dim3((env_end - env_begin + kTileM - 1) / kTileM);
   lc.blockDim = dim3(kThreads);
   lc.dynamicSmemBytes = kSmemBytes;
   lc.stream = stream;
@@ -332,6 +334,6 @@ cudaError_t fx_launch_policy(const CUtensorMap& map_obs, const CUtensorMap& map_
   at[0].val.programmaticStreamSerializationAllowed = 1;
   lc.attrs = at;
   lc.numAttrs = 1;
-  return cudaLaunchKernelEx(&lc, fx_policy_kernel, map_obs, map_w1, map_w2, pol, num_envs, k_pad / kBlockK, gumbel, seed, step,
-                            action, logp, value);
+  return cudaLaunchKernelEx(&lc, fx_policy_kernel, map_obs, map_w1, map_w2, pol, env_end, k_pad / kBlockK, gumbel, seed, step,
+                            action, logp, value, env_begin);
 }

@@ -23,7 +23,8 @@ cudaError_t fx_policy_configure();
 // gumbel: float32 [num_envs][3] Gumbel(0,1) noise, or nullptr for the in-kernel counter-based generator (seed, step).
 cudaError_t fx_launch_policy(const CUtensorMap& map_obs, const CUtensorMap& map_w1, const CUtensorMap& map_w2,
                              const FxPolicyDev& pol, int num_envs, int k_pad, const float* gumbel, unsigned long long seed,
-                             unsigned step, int32_t* action, float* logp, float* value, cudaStream_t stream);
+                             unsigned step, int32_t* action, float* logp, float* value, cudaStream_t stream,
+                             int env_begin = 0, int env_end = -1);  // env_begin must be a multiple of FX_POLICY_TILE_M
 
 // fp32 [rows][cols] (nn.Linear layout) -> bf16 [rows][cols_pad], zero padded
 cudaError_t fx_policy_pack(const float* src, uint16_t* dst, int rows, int cols, int cols_pad, cudaStream_t stream);
