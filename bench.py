@@ -262,11 +262,11 @@ def single_step_graph_rate(args, cfg, candles, minutes, N, starts, acts, ring, r
     import torch
     from gym_fx_b200.vec_env import VecFxEnv
 
-    os.environ["FXENV_DEBUG"] = "8"
+    os.environ["FXENV_ENGINE"] = "graph"
     try:
         env = VecFxEnv(cfg, candles, minutes, device=ring.device)
     finally:
-        del os.environ["FXENV_DEBUG"]
+        del os.environ["FXENV_ENGINE"]
     env.reset(starts)
     K = min(args.steps, 2 * chunk)
     reps = max(1, K // chunk)

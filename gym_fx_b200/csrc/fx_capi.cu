@@ -40,6 +40,7 @@ struct FxEnv {
   bool was_reset = false;
   bool first_reset = true;
   int timeline_steps = 0;
+  int force_engine = -1;           // FXENV_ENGINE (timing experiments): 0 graph of single steps, 1 persistent launch
   bool seq_tracked = true;         // fx_rollout_kernel's seq[] / ticket words hold (seq_base, ticket_base): no memset needed
   unsigned seq_base = 0u, ticket_base = 0u;
   int64_t launches = 0;
@@ -189,6 +190,7 @@ int fxenv_create(const FxConfig* cfg, FxEnv** out) {
       cudaMemset(env->P.timeline, 0, nb);
     }
   }
+  if (const char* fe = getenv("FXENV_ENGINE")) env->force_engine = (fe[0] == 'p') ? 1 : (fe[0] == 'g' ? 0 : -1);
   env->P.any_binary = 0;
   for (int i = 0; i < c.n_features; i++) if (c.feature_binary[i]) env->P.any_binary = 1;
   if (c.preproc != FX_PREPROC_FEATURE_WINDOW) env->P.any_binary = 0;
@@ -343,11 +345,12 @@ int fxenv_step(FxEnv* env, const void* actions_dev, float* obs_dev, float* rewar
 }
 
 static bool batch_uses_rollout(const FxEnv* env, int n_steps) {
-  // measured (B200, us/step persistent vs graph): W=128 rows (3.6 KB) at 2048 / 4096 / 8192 / 16384 envs: 10.2 vs 15.7,
-  // 12.5 vs 20.6, 24.8 vs 30.6, 52.0 vs 53.0; cfg3 (16384 envs, 7.2 KB rows) 77.6 vs 68.2; cfg5 (8192 envs, 14 KB rows)
-  // 75.7 vs 74.6 -- the persistent launch pays a store-drain fence per env-step that grows with the row size
-  const bool few_waves = (long long)env->P.cfg.num_envs <= 3ll * env->P.resident_blocks * FX_WARPS;
-  bool rollout = n_steps > 1 && (few_waves || env->P.obs_dim <= 1024);
+  // measured (B200, round 2, us/step persistent vs graph of single steps): cfg2 4096 envs 11.3 vs 24.7; cfg2 shape at 16384
+  // envs 47.9 vs 50.7; cfg3 (16384 envs, 7.2 KB rows) 70.3 vs 70.7; cfg5 (8192 envs, 14 KB rows) 78.9 vs 83.8 -- the
+  // persistent launch wins or ties everywhere, so every batch of more than one step uses it
+  bool rollout = n_steps > 1;
+  if (env->force_engine == 0) rollout = false;             // FXENV_ENGINE=graph / persistent: A/B of the engines
+  if (env->force_engine == 1 && n_steps > 1) rollout = true;
   if (env->P.debug & (4 | 8)) rollout = false;             // FXENV_DEBUG: force the graph of single steps (A/B timing)
   if ((env->P.debug & 16) && n_steps > 1) rollout = true;  // FXENV_DEBUG & 16: force the persistent launch
   return rollout;

@@ -332,7 +332,7 @@ __device__ __noinline__ void fx_emit_windows_t(const FxKernelParams& P, int lane
 // difference is far below half a float32 ulp).  prices | returns: a lane owns 4 consecutive rows.
 // PAD: the episode is younger than the window (s < W rows staged): output row w shows staged row max(0, w - pad), i.e. the
 // first row repeated `pad` times (feature_window_preprocessor.py:153-160,197-204) -- the first W steps of every episode.
-template <bool CLIP, bool TAME, bool O16, bool PAD>
+template <bool CLIP, bool TAME, bool O16, bool PAD, bool LONG>
 __device__ __noinline__ void fx_emit_fast5_q(const FxKernelParams& P, int lane, bool scale, const double* __restrict__ win,
                                              const double* sstat, float* __restrict__ out, uint16_t* __restrict__ o16_,
                                              const int pad) {
@@ -357,7 +357,9 @@ __device__ __noinline__ void fx_emit_fast5_q(const FxKernelParams& P, int lane, 
     }
     const int nq = (5 * W) >> 2;
     float4* __restrict__ o4 = reinterpret_cast<float4*>(out);
-#pragma unroll 1
+    // short windows: not unrolled -- the warps of an SM sit at different places of a large kernel, and the smaller loop
+    // body is worth more in instruction-cache hits than the saved loop overhead; LONG (W >= 384): unrolled by 2
+#pragma unroll(LONG ? 2 : 1)
     for (int q = lane; q < nq; q += 30) {
       double x[4];
       if (PAD) {  // element j of the block comes from staged element j - 5 * pad, or from row 0 (same feature) in the pad
@@ -408,8 +410,9 @@ __device__ __forceinline__ void fx_emit_windows(const FxKernelParams& P, int lan
   const int pad = P.cfg.window_size - s;  // > 0: the first rows of the window repeat the episode's first bar
   if (LEAN) {  // window % 4 == 0, price window, clip > 0 and finite data are part of the LEAN contract
     if ((reinterpret_cast<uintptr_t>(out) & 15) == 0) {
-      if (pad <= 0) fx_emit_fast5_q<true, true, O16, false>(P, lane, scale, win, sstat, out, o16, 0);
-      else fx_emit_fast5_q<true, true, O16, true>(P, lane, scale, win, sstat, out, o16, pad);
+      if (pad > 0) fx_emit_fast5_q<true, true, O16, true, false>(P, lane, scale, win, sstat, out, o16, pad);
+      else if (P.cfg.window_size >= 384) fx_emit_fast5_q<true, true, O16, false, true>(P, lane, scale, win, sstat, out, o16, 0);
+      else fx_emit_fast5_q<true, true, O16, false, false>(P, lane, scale, win, sstat, out, o16, 0);
     } else {
       fx_emit_windows_t<true, true, true, false, O16>(P, lane, s, scale, win, sstat, out, o16);
     }
@@ -417,8 +420,9 @@ __device__ __forceinline__ void fx_emit_windows(const FxKernelParams& P, int lan
   }
   if (FAST5 && (P.cfg.window_size & 3) == 0 && P.cfg.include_price_window && P.cfg.feature_clip > 0.0 && P.tame_data &&
       (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
-    if (pad <= 0) fx_emit_fast5_q<true, true, O16, false>(P, lane, scale, win, sstat, out, o16, 0);
-    else fx_emit_fast5_q<true, true, O16, true>(P, lane, scale, win, sstat, out, o16, pad);
+    if (pad > 0) fx_emit_fast5_q<true, true, O16, true, false>(P, lane, scale, win, sstat, out, o16, pad);
+    else if (P.cfg.window_size >= 384) fx_emit_fast5_q<true, true, O16, false, true>(P, lane, scale, win, sstat, out, o16, 0);
+    else fx_emit_fast5_q<true, true, O16, false, false>(P, lane, scale, win, sstat, out, o16, 0);
     return;
   }
   const bool lng = P.cfg.window_size >= 384;
@@ -1000,7 +1004,9 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
   asm volatile("griddepcontrol.launch_dependents;");
   fx_window_init(lane, ws);  // mbarrier init + fence
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  fx_step_env<STRAT, REWARD, FAST5, true, LEAN>(P, actions, obs, reward, reward64, terminated, env, lane, ws, 0u, 0u, 0u, obs16, stride16);
+  // the bf16 copy of the row (closed loop only) is a compile-time variant: no per-store pointer tests in the plain step
+  if (obs16) fx_step_env<STRAT, REWARD, FAST5, true, LEAN>(P, actions, obs, reward, reward64, terminated, env, lane, ws, 0u, 0u, 0u, obs16, stride16);
+  else fx_step_env<STRAT, REWARD, FAST5, false, LEAN>(P, actions, obs, reward, reward64, terminated, env, lane, ws);
 }
 
 // ---- K steps in ONE launch (fxenv_step_many): persistent warps pull (step, env) tickets ----------------------------

@@ -299,12 +299,12 @@ def test_step_many_rollout_kernel_matches_graph_of_steps(cfg2_full):
     starts = torch.as_tensor(start_offsets(N, T, 400, 256))
     acts = torch.randint(0, 3, (2, K, N), dtype=torch.int32, generator=torch.Generator().manual_seed(11)).cuda()
     outs = []
-    for dbg in ("16", "8"):  # 16: force the persistent launch, 8: force the graph of grid-serialised steps
-        os.environ["FXENV_DEBUG"] = dbg
+    for eng in ("persistent", "graph"):  # the persistent launch vs the graph of grid-serialised single steps
+        os.environ["FXENV_ENGINE"] = eng
         try:
             env = VecFxEnv(cfg, candles, minutes)
         finally:
-            del os.environ["FXENV_DEBUG"]
+            del os.environ["FXENV_ENGINE"]
         env.reset(starts)
         l0 = env.launch_count()
         ring = torch.zeros((3, N, env.obs_dim), dtype=torch.float32, device="cuda")
@@ -365,12 +365,12 @@ def test_step_many_engines_agree_on_other_kernels(case):
     starts = torch.as_tensor(start_offsets(N, T, 400, 300))
     acts = torch.randint(0, 3, (2, K, N), dtype=torch.int32, generator=torch.Generator().manual_seed(3)).cuda()
     outs = []
-    for dbg in ("16", "8"):
-        os.environ["FXENV_DEBUG"] = dbg
+    for eng in ("persistent", "graph"):
+        os.environ["FXENV_ENGINE"] = eng
         try:
             env = VecFxEnv(cfg, candles, minutes)
         finally:
-            del os.environ["FXENV_DEBUG"]
+            del os.environ["FXENV_ENGINE"]
         env.reset(starts)
         ring = torch.zeros((2, N, env.obs_dim), dtype=torch.float32, device="cuda")
         rews = torch.zeros((2, K, N), dtype=torch.float32, device="cuda")
@@ -396,11 +396,11 @@ def test_step_many_edge_sizes_match_single_steps(N, K):
     cfg, candles, minutes = _mk(cfgd, plugins, N, T=T, order_capacity=256, **kw)
     starts = torch.as_tensor(start_offsets(N, T, K + 10, 300))
     acts = torch.randint(0, 3, (K, N), dtype=torch.int32, generator=torch.Generator().manual_seed(N)).cuda()
-    os.environ["FXENV_DEBUG"] = "16"
+    os.environ["FXENV_ENGINE"] = "persistent"
     try:
         many = VecFxEnv(cfg, candles, minutes)
     finally:
-        del os.environ["FXENV_DEBUG"]
+        del os.environ["FXENV_ENGINE"]
     single = VecFxEnv(cfg, candles, minutes)
     many.reset(starts); single.reset(starts)
     assert many.step_many_engine(K) == "persistent"
@@ -420,8 +420,7 @@ def test_step_many_edge_sizes_match_single_steps(N, K):
     ("cfg5_atr_fw512_sharpe_4pairs", 8192, None),           # BASELINE configs[4] (per GPU) at full size
 ])
 def test_full_size_other_baseline_shapes(case, N, pairs_kw):
-    """At BASELINE's full sizes for the two large shapes: a batch through fxenv_step_many (the graph engine at these
-    sizes) is reproducible, independent of how many envs share the launch (every 16th env run alone gives the same
+    """At BASELINE's full sizes for the two large shapes: a batch through fxenv_step_many is reproducible, independent of how many envs share the launch (every 16th env run alone gives the same
     trajectory), keeps equity under the flat policy, and a sample of 48 envs matches the CPU oracle step by step."""
     from gym_fx_b200.vec_env import VecFxEnv
     cfgd, plugins, kw = VEC_CASES[case]
@@ -446,7 +445,7 @@ def test_full_size_other_baseline_shapes(case, N, pairs_kw):
 
     allenv = np.arange(N)
     ((obs, obs_all_steps), rews, terms, inf, engine), _ = run(allenv, acts)
-    assert engine == "graph" and not np.any(inf["flags"] & 16)
+    assert engine == "persistent" and not np.any(inf["flags"] & 16)
     ((obs2, obs_all_steps2), rews2, terms2, inf2, _), _ = run(allenv, acts)
     assert np.array_equal(obs, obs2) and np.array_equal(rews, rews2) and np.array_equal(inf["equity"], inf2["equity"])
     assert np.array_equal(obs_all_steps, obs_all_steps2)

@@ -9,7 +9,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O
 nproc > $OUT/nproc.txt
 for w in $WHAT; do case $w in
 smoke) timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1; echo "smoke rc=$?" ;;
-tests) timeout 900 python -m pytest tests -m gpu -q -p no:cacheprovider --timeout 600 > $OUT/pytest.log 2>&1; echo "pytest rc=$?"; tail -25 $OUT/pytest.log ;;
+tests) timeout 900 python -m pytest tests -m gpu -q -p no:cacheprovider --timeout 180 > $OUT/pytest.log 2>&1; echo "pytest rc=$?"; tail -25 $OUT/pytest.log ;;
 ksweep) for k in 20 32 128 1000; do
          timeout 300 python bench.py --steps $k --warmup 5 --no-cpu-baseline --no-single-step --no-closed-loop --no-other-workloads > $OUT/bench_cfg2_k$k.json 2> $OUT/bench_cfg2_k$k.err
          python -c "import json,sys; d=json.load(open('$OUT/bench_cfg2_k$k.json')); print('K=%-5d %7.2f us/step  %7.1f M steps/s  frac %.3f  e2e %.2f M' % ($k, d['ms_per_step']*1e3, d['value']/1e6, d['roofline']['frac'], d['e2e']['value']/1e6))"; done ;;
