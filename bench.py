@@ -83,10 +83,19 @@ def build_workload(name, envs_per_gpu=None, n_shards=1):
     return cfg, candles, minutes, envs, D, algo_bytes, desc
 
 
-def common_config(desc, envs_per_gpu, D, world):
+def preroll_steps(cfg):
+    """Untimed steps every episode is advanced by before the warm-up, so that the measured steps are the ones an episode
+    consists of (the tables hold 2^19 bars): windows full, z-score statistics from the full rolling window.  The first
+    max(window, scaling_window) steps of an episode run the padded-window / running-statistics paths instead."""
+    return int(max(cfg.window_size, cfg.scaling_window if cfg.scaling != 0 else 0)) + 16
+
+
+def common_config(desc, envs_per_gpu, D, world, preroll):
     """The `config` object of the JSON line: identical for both arms (`--impl ours` / `--impl reference`) of one run."""
     return {"workload": desc, "envs_per_gpu": envs_per_gpu, "obs_dim": D, "parallelism": f"env-shard x{world}",
-            "actions": "uniform {0,1,2}, i.i.d. per env-step, seeded", "auto_reset": True}
+            "actions": "uniform {0,1,2}, i.i.d. per env-step, seeded", "auto_reset": True,
+            "episode_phase": f"steady state: every episode advanced {preroll} untimed steps (> window, scaling window) "
+                             "before the warm-up steps"}
 
 
 def pin_to_gpu_numa_node(local_rank):
@@ -209,11 +218,14 @@ def cpu_port_rate(workload, total_envs, steps, warmup, threads, budget_s=None):
 
     cfg, candles, minutes, envs, D, _, desc = build_workload(workload, total_envs)
     vec = OracleVec(cfg, candles, minutes)
-    vec.reset(start_offsets(total_envs, T_BARS, steps + warmup + 64, 256))
+    pre = preroll_steps(cfg)
+    vec.reset(start_offsets(total_envs, T_BARS, steps + warmup + pre + 64, 256))
     ps = ParallelStepper(vec, threads)
     rng = np.random.default_rng(1234)
     chunk = 8
     acts = rng.integers(0, 3, (chunk, total_envs)).astype(np.int32)
+    for _ in range(-(-pre // chunk)):        # same episode phase as the GPU arm (preroll_steps)
+        ps.run(acts)
     if warmup:
         ps.run(acts[:min(warmup, chunk)])
     t0 = time.perf_counter()
@@ -226,7 +238,7 @@ def cpu_port_rate(workload, total_envs, steps, warmup, threads, budget_s=None):
             break
     dt = time.perf_counter() - t0
     vec.close()
-    return total_envs * done / dt, done, dt, ps.threads, desc
+    return total_envs * done / dt, done, dt, ps.threads, desc, pre
 
 
 def run_reference(args, rank, world):
@@ -236,13 +248,13 @@ def run_reference(args, rank, world):
     threads = os.cpu_count() or 1
     envs_per_gpu = args.envs or WORKLOADS[args.workload][0]
     total = envs_per_gpu * args.gpus
-    rate, done, dt, used, _ = cpu_port_rate(args.workload, total, args.steps, args.warmup, threads)
+    rate, done, dt, used, _, pre = cpu_port_rate(args.workload, total, args.steps, args.warmup, threads)
     _, _, _, _, D, _, desc = build_workload(args.workload, envs_per_gpu)
     line = {
         "impl": "reference", "metric": "env-steps/sec", "value": rate, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": done, "warmup": args.warmup, "ms_per_step": dt / done * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": common_config(desc, envs_per_gpu, D, args.gpus),
+        "config": common_config(desc, envs_per_gpu, D, args.gpus, pre),
         "details": {"total_envs": total,
                     "note": "CPU arm: C port of the reference path (oracle/fxenv_oracle.c) stepping the envs of all "
                             f"{args.gpus} GPU shard(s) on this host; the Python reference (measured in the build container "
@@ -294,7 +306,8 @@ def short_workload_rate(name, K, dev):
 
     cfg, candles, minutes, N, D, algo_bytes, desc = build_workload(name)
     env = VecFxEnv(cfg, candles, minutes, device=dev)
-    env.reset(torch.as_tensor(shard_starts(N, 0, 1, T_BARS, 2 * K + 64, 256)))
+    pre = preroll_steps(cfg)
+    env.reset(torch.as_tensor(shard_starts(N, 0, 1, T_BARS, 2 * K + pre + K + 64, 256)))
     gen = torch.Generator(device=dev)
     gen.manual_seed(4321)
     acts = torch.randint(0, 3, (K, N), generator=gen, device=dev, dtype=torch.int32)
@@ -303,7 +316,8 @@ def short_workload_rate(name, K, dev):
     rews = torch.empty((K, N), dtype=torch.float32, device=dev)
     terms = torch.empty((K, N), dtype=torch.uint8, device=dev)
     plan = env.plan_step_many(acts, ring, rews, terms)
-    plan()                                   # warm-up: K >= 3 steps, instantiates the graph if that engine is used
+    for _ in range(-(-pre // K) + 1):       # episodes into steady state, then the warm-up: K >= 3 steps
+        plan()
     torch.cuda.synchronize(dev)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -334,7 +348,16 @@ def closed_loop_block(K, rank, world, dev, dist):
     env = VecFxEnv(cfg, candles, minutes, device=dev)
     H = max(2, min(32, K))
     reps = max(1, min(8, K // H))
-    env.reset(torch.as_tensor(shard_starts(N, rank, world, T_BARS, (reps + 3) * H + 64, 256)))
+    pre = preroll_steps(cfg)
+    env.reset(torch.as_tensor(shard_starts(N, rank, world, T_BARS, (reps + 3) * H + pre + 128, 256)))
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(77 + rank)
+    pa = torch.randint(0, 3, (64, N), generator=gen, device=dev, dtype=torch.int32)
+    pring = torch.empty((2, N, D), dtype=torch.float32, device=dev)
+    prew, pterm = torch.empty((64, N), dtype=torch.float32, device=dev), torch.empty((64, N), dtype=torch.uint8, device=dev)
+    for _ in range(-(-pre // 64)):                           # episodes into steady state (preroll_steps), random actions
+        env.step_many(pa, pring, prew, pterm)
+    del pring
     torch.manual_seed(0)                                     # identical replicas on every rank
     torch.backends.cuda.matmul.allow_tf32 = True
     net = ActorCritic(D).to(dev)
@@ -404,11 +427,12 @@ def run_ours(args, rank, world, local_rank):
     env = VecFxEnv(cfg, candles, minutes, device=dev)
     # envs are sharded by rank: global env id = rank * N + i (no collective in the data path)
     check_pair_alignment(N, cfg.num_pairs)
-    starts = torch.as_tensor(shard_starts(N, rank, world, T_BARS, K + Wm + 64, 256))
+    pre = preroll_steps(cfg)
+    chunk = min(K, 500)                      # steps per fxenv_step_many batch; K = full batches + one remainder batch
+    starts = torch.as_tensor(shard_starts(N, rank, world, T_BARS, K + Wm + pre + 3 * chunk + 464, 256))
     env.reset(starts)
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
-    chunk = min(K, 500)                      # steps per fxenv_step_many batch; K = full batches + one remainder batch
     acts = torch.randint(0, 3, (chunk, N), generator=gen, device=dev, dtype=torch.int32)
     slots = max(2, -(-int(L2_BYTES * 1.8) // (N * D * 4)))  # ring > 1.8x L2 so stores cannot just sit in L2
     ring = torch.empty((slots, N, D), dtype=torch.float32, device=dev)
@@ -421,7 +445,9 @@ def run_ours(args, rank, world, local_rank):
     rem = K % chunk
     tail = env.plan_step_many(acts[:rem], ring, rews[:rem], terms[:rem]) if rem else None
 
-    # warm-up (also instantiates the graph)
+    # episodes into steady state (preroll_steps), then the warm-up (also instantiates the graph)
+    for _ in range(-(-pre // chunk)):
+        full()
     wchunks = -(-Wm // chunk)
     for _ in range(max(1, wchunks)):
         full()
@@ -497,7 +523,7 @@ def run_ours(args, rank, world, local_rank):
             "metric": "env-steps/sec", "value": N * world * K / (ms_max * 1e-3), "unit": "env-steps/s",
             "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms_max / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": common_config(desc, N, D, world),
+            "config": common_config(desc, N, D, world, pre),
             "details": {"actions": "torch.Generator(seed=1234+rank), pre-generated on device",
                         "l2": f"obs rows rotate through a {slots}-slot ring ({slots * N * D * 4 / 2**20:.0f} MiB > 126 MiB L2)",
                         "engine": (f"persistent launch: {chunk} steps per launch, warps pull (step, env) tickets, per-env dependencies"
@@ -523,7 +549,7 @@ def run_ours(args, rank, world, local_rank):
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             sample_envs = min(N, 4096)
-            rate, done, dt, used, _ = cpu_port_rate(args.workload, sample_envs, 100000, 3, threads, budget_s=8.0)
+            rate, done, dt, used, _, _ = cpu_port_rate(args.workload, sample_envs, 100000, 3, threads, budget_s=8.0)
             line["cpu_baseline"] = {"value": rate, "unit": "env-steps/s", "cores": used, "kind": "port",
                                     "sample": f"{sample_envs} envs x {done} steps ({dt:.1f} s), C oracle port, {used} host threads, "
                                               f"no per-step barrier"}

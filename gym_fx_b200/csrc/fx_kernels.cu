@@ -26,6 +26,8 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "fx_kernels.cuh"
 
 #define FX_FULL 0xffffffffu
@@ -1009,15 +1011,17 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
   else fx_step_env<STRAT, REWARD, FAST5, false, LEAN>(P, actions, obs, reward, reward64, terminated, env, lane, ws);
 }
 
-// ---- K steps in ONE launch (fxenv_step_many): persistent warps pull (step, env) tickets ----------------------------
+// ---- K steps in ONE launch (fxenv_step_many): persistent warps pull (step chunk, env) tickets ----------------------
 // The actions of the whole batch are supplied up front, so an env only depends on ITS OWN previous step.  A grid that
 // fits the device at once keeps every warp slot busy for the whole batch: a warp takes the next ticket g from a
-// global counter (step k = g / N, env = g % N: all envs of step k are handed out before step k+1), waits until
-// seq[env] == k (acquire; the warp that finished the env's previous step released it), runs the env-step, publishes
-// seq[env] = k + 1 (release).  No kernel boundary, CTA turnaround or grid-wide barrier between steps; heavy env-steps
-// (many fills) only delay their own env.  No deadlock: the ticket an env-step waits for is lower than its own, and every
-// ticket handed out belongs to a running warp that needs nothing from higher tickets.  seq[] and the counter are zeroed
-// by a stream-ordered memset before the launch.
+// global counter (chunk ch = g / N, env = g % N: all envs of a chunk are handed out before the next chunk), waits until
+// seq[env] == ch * chunk (acquire; the warp that ran the env's previous chunk released it), runs `chunk` consecutive
+// steps of that env, publishes seq[env] = first step of the next chunk (release).  No kernel boundary, CTA turnaround
+// or grid-wide barrier between steps; heavy env-steps (many fills) only delay their own env.  The hand-over between
+// warps costs a fence that drains the row's streaming stores, the sequence-word store and an acquire round trip
+// (~20 % of a step at chunk = 1): the chunk length amortises it (fx_rollout_chunk).  No deadlock: the ticket an env-step
+// waits for is lower than its own, and every ticket handed out belongs to a running warp that needs nothing from higher
+// tickets.  seq[] and the counter are epoch-based (see below), or zeroed by a stream-ordered memset inside captures.
 #ifndef FX_ROLLOUT_MIN_BLOCKS
 #define FX_ROLLOUT_MIN_BLOCKS FX_MIN_BLOCKS
 #endif
@@ -1025,7 +1029,7 @@ template <int STRAT, int REWARD, bool FAST5, bool LEAN>
 __global__ void __launch_bounds__(FX_WARPS * 32, FX_ROLLOUT_MIN_BLOCKS)
 fx_rollout_kernel(const __grid_constant__ FxKernelParams P, const char* __restrict__ actions, float* __restrict__ obs,
                   const int obs_slots, float* __restrict__ reward, uint8_t* __restrict__ terminated, const int n_steps,
-                  const unsigned seq_base, const unsigned ticket_base) {
+                  const int chunk, const unsigned seq_base, const unsigned ticket_base) {
   extern __shared__ __align__(16) unsigned char fx_smem[];
   const FxConfig& c = P.cfg;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1035,7 +1039,7 @@ fx_rollout_kernel(const __grid_constant__ FxKernelParams P, const char* __restri
   asm volatile("griddepcontrol.launch_dependents;");  // the next batch's launch latency hides behind this one
   fx_window_init(lane, ws);
   const unsigned N = (unsigned)c.num_envs;
-  const unsigned total = N * (unsigned)n_steps;  // < 2^31 (checked by the caller)
+  const unsigned total = N * (unsigned)((n_steps + chunk - 1) / chunk);  // tickets; N * n_steps < 2^31 (checked by the caller)
   unsigned* ticket = reinterpret_cast<unsigned*>(P.seq + N);
   asm volatile("griddepcontrol.wait;" ::: "memory");  // everything below touches memory the previous launch wrote
   // seq[] and the ticket counter are never reset: this launch's values start at seq_base / ticket_base (kept by the
@@ -1049,23 +1053,31 @@ fx_rollout_kernel(const __grid_constant__ FxKernelParams P, const char* __restri
     // the ticket after this one is requested now: its atomic round trip hides behind the env-step
     unsigned g_next = 0u;
     if (lane == 0) g_next = atomicAdd(ticket, 1u) - ticket_base;
-    const unsigned k = g / N, env = g - k * N;
+    const unsigned ch = g / N, env = g - ch * N;
+    unsigned k = ch * (unsigned)chunk;
+    unsigned k_end = k + (unsigned)chunk;
+    if (k_end > (unsigned)n_steps) k_end = (unsigned)n_steps;
     if (k > 0u) {
       if (lane == 0) { while ((unsigned)fx_ld_acquire(P.seq + env) != seq_base + k) __nanosleep(32); }
       __syncwarp();
     }
+    // the warp keeps the env for `chunk` consecutive steps: between them the state goes through memory as always, but
+    // within one warp (__syncwarp orders it) -- no fence, no sequence word, no acquire round trip
+#pragma unroll 1
+    for (; k < k_end; ++k) {
 #if defined(FXENV_ENABLE_TIMING) || defined(FXENV_ENABLE_TIMELINE)
-    if (P.timeline && lane == 0) { long long g__; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g__)); P.timeline[((size_t)k * N + env) * 2] = g__; }
+      if (P.timeline && lane == 0) { long long g__; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g__)); P.timeline[((size_t)k * N + env) * 2] = g__; }
 #endif
-    fx_step_env<STRAT, REWARD, FAST5, false, LEAN>(P, actions, obs, reward, nullptr, terminated, (int)env, lane, ws, phase, k * N,
-                                      (k % (unsigned)obs_slots) * N);
-    __syncwarp();
-    if (lane == 0) fx_st_release(P.seq + env, (int)(seq_base + k + 1u));
+      fx_step_env<STRAT, REWARD, FAST5, false, LEAN>(P, actions, obs, reward, nullptr, terminated, (int)env, lane, ws, phase, k * N,
+                                        (k % (unsigned)obs_slots) * N);
+      __syncwarp();
+      phase++;
 #if defined(FXENV_ENABLE_TIMING) || defined(FXENV_ENABLE_TIMELINE)
-    if (P.timeline && lane == 0) { long long g__; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g__)); P.timeline[((size_t)k * N + env) * 2 + 1] = g__; }
+      if (P.timeline && lane == 0) { long long g__; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g__)); P.timeline[((size_t)k * N + env) * 2 + 1] = g__; }
 #endif
+    }
+    if (lane == 0) fx_st_release(P.seq + env, (int)(seq_base + k_end));
     g = __shfl_sync(FX_FULL, g_next, 0);
-    phase++;
   }
 }
 
@@ -1154,7 +1166,7 @@ __global__ void fx_stats_kernel(FxConfig c, const double* __restrict__ candles, 
 }
 
 typedef void (*StepKernel)(const FxKernelParams, const void*, float*, float*, double*, uint8_t*, int, int, uint16_t*, int);
-typedef void (*RolloutKernel)(const FxKernelParams, const char*, float*, int, float*, uint8_t*, int, unsigned, unsigned);
+typedef void (*RolloutKernel)(const FxKernelParams, const char*, float*, int, float*, uint8_t*, int, int, unsigned, unsigned);
 
 // mode: 0 = general features, 1 = 5-feature fast path, 2 = LEAN (implies the 5-feature fast path)
 template <int STRAT, int REWARD>
@@ -1283,12 +1295,32 @@ int fx_rollout_blocks(const FxKernelParams& P) {
   return blocks > P.resident_blocks ? P.resident_blocks : blocks;
 }
 
+// Steps per ticket of fx_rollout_kernel.  A longer chunk removes hand-overs (fence + sequence word + acquire round trip
+// per step) but coarsens the work units: keep >= 6 tickets per resident warp so that the tail of the batch stays short
+// (measured, cfg2 at 4096 envs, us/step: 11.96 at chunk 1, 11.1 at 4, 9.6 at 16, 9.25 at 32..64, 10.3 at 250 of 500).
+// When every env has a warp of its own the whole batch is one chunk: no hand-over at all.  FXENV_CHUNK overrides.
+int fx_rollout_chunk(const FxKernelParams& P, int n_steps) {
+  const char* fe = getenv("FXENV_CHUNK");  // read per launch: tests switch it between batches
+  const int forced = fe ? atoi(fe) : 0;
+  int chunk;
+  if (forced > 0) chunk = forced;
+  else {
+    const long long warps = (long long)fx_rollout_blocks(P) * FX_WARPS;
+    const long long N = P.cfg.num_envs;
+    if (N <= warps) chunk = n_steps;
+    else { chunk = (int)((N * (long long)n_steps) / (warps * 6)); if (chunk > 64) chunk = 64; }
+  }
+  if (chunk < 1) chunk = 1;
+  if (chunk > n_steps) chunk = n_steps;
+  return chunk;
+}
+
 // seq_base / ticket_base: the values seq[] and the ticket counter hold when this launch starts (see fx_rollout_kernel);
 // reset_words: zero them first with a stream-ordered memset (then both bases must be 0) -- used inside stream captures,
 // where the host cannot track what the counters will hold at replay time.
 cudaError_t fx_launch_rollout(const FxKernelParams& P, const void* actions, float* obs, int obs_slots, float* reward,
-                              uint8_t* terminated, int n_steps, unsigned seq_base, unsigned ticket_base, bool reset_words,
-                              cudaStream_t stream) {
+                              uint8_t* terminated, int n_steps, int chunk, unsigned seq_base, unsigned ticket_base,
+                              bool reset_words, cudaStream_t stream) {
   const int N = P.cfg.num_envs;
   if (reset_words) {
     cudaError_t e = cudaMemsetAsync(P.seq, 0, ((size_t)N + 1) * sizeof(int32_t), stream);
@@ -1305,7 +1337,7 @@ cudaError_t fx_launch_rollout(const FxKernelParams& P, const void* actions, floa
   lc.attrs = at;
   lc.numAttrs = (reset_words || (P.debug & 4)) ? 0 : 1;  // behind a memset node: plain stream order
   return cudaLaunchKernelEx(&lc, pick_rollout(P), P, reinterpret_cast<const char*>(actions), obs, obs_slots, reward,
-                            terminated, n_steps, seq_base, ticket_base);
+                            terminated, n_steps, chunk, seq_base, ticket_base);
 }
 
 cudaError_t fx_launch_reset(const FxKernelParams& P, const int64_t* start_bar, const uint8_t* mask, int first,

@@ -88,6 +88,7 @@ cudaError_t fx_launch_stats(const FxConfig& cfg, const double* candles, double* 
 cudaError_t fx_configure_kernels(FxKernelParams& P);
 bool fx_config_is_lean(const FxKernelParams& P);
 cudaError_t fx_launch_rollout(const FxKernelParams& P, const void* actions, float* obs, int obs_slots, float* reward,
-                              uint8_t* terminated, int n_steps, unsigned seq_base, unsigned ticket_base, bool reset_words,
-                              cudaStream_t stream);
+                              uint8_t* terminated, int n_steps, int chunk, unsigned seq_base, unsigned ticket_base,
+                              bool reset_words, cudaStream_t stream);
 int fx_rollout_blocks(const FxKernelParams& P);
+int fx_rollout_chunk(const FxKernelParams& P, int n_steps);  // steps per ticket (the host's ticket accounting needs it)

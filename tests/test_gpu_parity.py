@@ -415,6 +415,43 @@ def test_step_many_edge_sizes_match_single_steps(N, K):
     many.close(); single.close()
 
 
+@pytest.mark.parametrize("chunk", [1, 3, 7, 64])
+def test_step_many_ticket_chunk_lengths_agree(chunk):
+    """fx_rollout_kernel hands a warp `chunk` consecutive steps of an env per ticket (fx_rollout_chunk; FXENV_CHUNK forces
+    a length).  More envs than resident warps, a batch length that no chunk divides, a 3-slot observation ring, two
+    batches back to back (epoch-based sequence words), auto-reset inside the batch: every chunk length gives the results
+    of the graph of single steps, bit for bit."""
+    import os
+    from gym_fx_b200.vec_env import VecFxEnv
+    cfgd, plugins, kw = VEC_CASES["cfg2_fixed_fw128_pnl"]
+    N, T, K = 5000, 4000, 23
+    cfg, candles, minutes = _mk(cfgd, plugins, N, T=T, order_capacity=256, auto_reset=True, episode_bars=40, **kw)
+    starts = torch.as_tensor(start_offsets(N, T, 200, 300))
+    acts = torch.randint(0, 3, (2, K, N), dtype=torch.int32, generator=torch.Generator().manual_seed(11)).cuda()
+    outs = []
+    for eng in ("persistent", "graph"):
+        os.environ["FXENV_ENGINE"] = eng
+        if eng == "persistent":
+            os.environ["FXENV_CHUNK"] = str(chunk)
+        try:
+            env = VecFxEnv(cfg, candles, minutes)
+            env.reset(starts)
+            ring = torch.zeros((3, N, env.obs_dim), dtype=torch.float32, device="cuda")
+            rews = torch.zeros((2, K, N), dtype=torch.float32, device="cuda")
+            terms = torch.zeros((2, K, N), dtype=torch.uint8, device="cuda")
+            for b in range(2):
+                env.step_many(acts[b], ring, rews[b], terms[b])
+            torch.cuda.synchronize()
+        finally:
+            del os.environ["FXENV_ENGINE"]
+            os.environ.pop("FXENV_CHUNK", None)
+        outs.append((ring, rews, terms, env.get_state()))
+        env.close()
+    a, b = outs
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]) and bytes(a[3]) == bytes(b[3])
+    assert int(a[2].sum()) >= N   # every env ended (and restarted) inside the batches
+
+
 @pytest.mark.parametrize("case,N,pairs_kw", [
     ("cfg3_atr_fw256_dd", 16384, {}),                       # BASELINE configs[2] at full size
     ("cfg5_atr_fw512_sharpe_4pairs", 8192, None),           # BASELINE configs[4] (per GPU) at full size
