@@ -462,6 +462,10 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.synchronize(dev)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     nfull = K // chunk
+    # the device spins ~50 us while the host enqueues the start event and the first launch: the timed region starts with
+    # the launch already queued, as it is for every launch after the first in a training loop (host launch latency is
+    # not device time of the K steps; without this a 20-step run carries ~10 us of it)
+    torch.cuda._sleep(100_000)
     ev0.record(stream)
     for _ in range(nfull):
         full()
@@ -526,7 +530,7 @@ def run_ours(args, rank, world, local_rank):
             "config": common_config(desc, N, D, world, pre),
             "details": {"actions": "torch.Generator(seed=1234+rank), pre-generated on device",
                         "l2": f"obs rows rotate through a {slots}-slot ring ({slots * N * D * 4 / 2**20:.0f} MiB > 126 MiB L2)",
-                        "engine": (f"persistent launch: {chunk} steps per launch, warps pull (step, env) tickets, per-env dependencies"
+                        "engine": (f"persistent launch: {chunk} steps per launch, warps pull (round of steps, env) tickets, per-env dependencies"
                                    if engine == "persistent" else f"CUDA graph of {chunk} single-step launches (programmatic dependent launch)"),
                         "order_overflow_envs": overflow, "terminated_frac": term_frac, "numa": numa},
             "clocks": clocks,

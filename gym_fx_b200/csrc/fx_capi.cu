@@ -394,12 +394,12 @@ int fxenv_step_many(FxEnv* env, int n_steps, const void* actions_dev, float* obs
     if (rcs != cudaStreamCaptureStatusNone) env->seq_tracked = false;
     const bool tracked = env->seq_tracked;
     if (env->P.timeline && n_steps > env->timeline_steps) return fail(env, FXENV_E_INVALID, "FXENV_TIMELINE smaller than n_steps");
-    const int chunk = fx_rollout_chunk(env->P, n_steps);
-    FX_CUDA(env, fx_launch_rollout(env->P, actions_dev, obs_dev, obs_slots, reward_dev, terminated_dev, n_steps, chunk,
+    const FxChunkPlan plan = fx_rollout_plan(env->P, n_steps);
+    FX_CUDA(env, fx_launch_rollout(env->P, actions_dev, obs_dev, obs_slots, reward_dev, terminated_dev, plan,
                                    tracked ? env->seq_base : 0u, tracked ? env->ticket_base : 0u, !tracked, stream));
     if (tracked) {
       env->seq_base += (unsigned)n_steps;
-      env->ticket_base += (unsigned)(N * (size_t)((n_steps + chunk - 1) / chunk)) + (unsigned)(fx_rollout_blocks(env->P) * FX_WARPS);
+      env->ticket_base += (unsigned)(N * (size_t)plan.n_rounds) + (unsigned)(fx_rollout_blocks(env->P) * FX_WARPS);
     }
     env->launches += 1;
     return FXENV_OK;

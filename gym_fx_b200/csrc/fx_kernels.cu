@@ -1014,12 +1014,12 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
 // ---- K steps in ONE launch (fxenv_step_many): persistent warps pull (step chunk, env) tickets ----------------------
 // The actions of the whole batch are supplied up front, so an env only depends on ITS OWN previous step.  A grid that
 // fits the device at once keeps every warp slot busy for the whole batch: a warp takes the next ticket g from a
-// global counter (chunk ch = g / N, env = g % N: all envs of a chunk are handed out before the next chunk), waits until
-// seq[env] == ch * chunk (acquire; the warp that ran the env's previous chunk released it), runs `chunk` consecutive
-// steps of that env, publishes seq[env] = first step of the next chunk (release).  No kernel boundary, CTA turnaround
+// global counter (round ch = g / N, env = g % N: all envs of a round are handed out before the next round), waits until
+// seq[env] == first step of the round (acquire; the warp that ran the env's previous round released it), runs the round's
+// consecutive steps of that env (FxChunkPlan), publishes seq[env] = first step of the next round (release).  No kernel boundary, CTA turnaround
 // or grid-wide barrier between steps; heavy env-steps (many fills) only delay their own env.  The hand-over between
 // warps costs a fence that drains the row's streaming stores, the sequence-word store and an acquire round trip
-// (~20 % of a step at chunk = 1): the chunk length amortises it (fx_rollout_chunk).  No deadlock: the ticket an env-step
+// (~20 % of a step at chunk = 1): the chunk length amortises it (fx_rollout_plan).  No deadlock: the ticket an env-step
 // waits for is lower than its own, and every ticket handed out belongs to a running warp that needs nothing from higher
 // tickets.  seq[] and the counter are epoch-based (see below), or zeroed by a stream-ordered memset inside captures.
 #ifndef FX_ROLLOUT_MIN_BLOCKS
@@ -1028,8 +1028,8 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
 template <int STRAT, int REWARD, bool FAST5, bool LEAN>
 __global__ void __launch_bounds__(FX_WARPS * 32, FX_ROLLOUT_MIN_BLOCKS)
 fx_rollout_kernel(const __grid_constant__ FxKernelParams P, const char* __restrict__ actions, float* __restrict__ obs,
-                  const int obs_slots, float* __restrict__ reward, uint8_t* __restrict__ terminated, const int n_steps,
-                  const int chunk, const unsigned seq_base, const unsigned ticket_base) {
+                  const int obs_slots, float* __restrict__ reward, uint8_t* __restrict__ terminated,
+                  const __grid_constant__ FxChunkPlan plan, const unsigned seq_base, const unsigned ticket_base) {
   extern __shared__ __align__(16) unsigned char fx_smem[];
   const FxConfig& c = P.cfg;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1039,7 +1039,7 @@ fx_rollout_kernel(const __grid_constant__ FxKernelParams P, const char* __restri
   asm volatile("griddepcontrol.launch_dependents;");  // the next batch's launch latency hides behind this one
   fx_window_init(lane, ws);
   const unsigned N = (unsigned)c.num_envs;
-  const unsigned total = N * (unsigned)((n_steps + chunk - 1) / chunk);  // tickets; N * n_steps < 2^31 (checked by the caller)
+  const unsigned total = N * (unsigned)plan.n_rounds;  // tickets; N * n_steps < 2^31 (checked by the caller)
   unsigned* ticket = reinterpret_cast<unsigned*>(P.seq + N);
   asm volatile("griddepcontrol.wait;" ::: "memory");  // everything below touches memory the previous launch wrote
   // seq[] and the ticket counter are never reset: this launch's values start at seq_base / ticket_base (kept by the
@@ -1054,9 +1054,9 @@ fx_rollout_kernel(const __grid_constant__ FxKernelParams P, const char* __restri
     unsigned g_next = 0u;
     if (lane == 0) g_next = atomicAdd(ticket, 1u) - ticket_base;
     const unsigned ch = g / N, env = g - ch * N;
-    unsigned k = ch * (unsigned)chunk;
-    unsigned k_end = k + (unsigned)chunk;
-    if (k_end > (unsigned)n_steps) k_end = (unsigned)n_steps;
+    unsigned k, k_end;  // the steps of round ch (FxChunkPlan)
+    if (ch < (unsigned)plan.n_uniform) { k = ch * (unsigned)plan.chunk; k_end = k + (unsigned)plan.chunk; }
+    else { k = (unsigned)plan.tail_start[ch - plan.n_uniform]; k_end = (unsigned)plan.tail_start[ch - plan.n_uniform + 1]; }
     if (k > 0u) {
       if (lane == 0) { while ((unsigned)fx_ld_acquire(P.seq + env) != seq_base + k) __nanosleep(32); }
       __syncwarp();
@@ -1166,7 +1166,7 @@ __global__ void fx_stats_kernel(FxConfig c, const double* __restrict__ candles, 
 }
 
 typedef void (*StepKernel)(const FxKernelParams, const void*, float*, float*, double*, uint8_t*, int, int, uint16_t*, int);
-typedef void (*RolloutKernel)(const FxKernelParams, const char*, float*, int, float*, uint8_t*, int, int, unsigned, unsigned);
+typedef void (*RolloutKernel)(const FxKernelParams, const char*, float*, int, float*, uint8_t*, const FxChunkPlan, unsigned, unsigned);
 
 // mode: 0 = general features, 1 = 5-feature fast path, 2 = LEAN (implies the 5-feature fast path)
 template <int STRAT, int REWARD>
@@ -1295,31 +1295,40 @@ int fx_rollout_blocks(const FxKernelParams& P) {
   return blocks > P.resident_blocks ? P.resident_blocks : blocks;
 }
 
-// Steps per ticket of fx_rollout_kernel.  A longer chunk removes hand-overs (fence + sequence word + acquire round trip
-// per step) but coarsens the work units: keep >= 6 tickets per resident warp so that the tail of the batch stays short
-// (measured, cfg2 at 4096 envs, us/step: 11.96 at chunk 1, 11.1 at 4, 9.6 at 16, 9.25 at 32..64, 10.3 at 250 of 500).
-// When every env has a warp of its own the whole batch is one chunk: no hand-over at all.  FXENV_CHUNK overrides.
-int fx_rollout_chunk(const FxKernelParams& P, int n_steps) {
+// The rounds of a batch (FxChunkPlan): every ticket of round r is one env for the steps [start_r, start_{r+1}).  A longer
+// chunk removes hand-overs (fence + sequence word + acquire round trip per ticket, ~2 us: ~20 % of a step at chunk = 1;
+// measured, cfg2 at 4096 envs, us/step: 11.96 at chunk 1, 11.1 at 4, 9.6 at 16, 9.25 at 32..64, 10.3 at 250 of 500) but
+// coarsens the work units: uniform chunks that leave >= 6 tickets per resident warp, at most 64 steps, the remainder as a
+// shorter last round.  Uniform rounds dealt in env order are work-conserving: an env's previous ticket finished
+// (N - warps) tickets ago, so nobody waits.  (Rounds that shrink towards the end of the batch -- "guided" scheduling, to
+// shorten the tail in which warps run dry -- were measured: 240 vs 247 us at 20 steps, but 448 vs 431 at 40 and 1055 vs
+// 1000 at 100; the extra hand-overs cost more than the tail.)  When every env has a warp of its own the whole batch is
+// one round: no hand-over at all.  FXENV_CHUNK=c forces chunks of c steps (measurements, tests).
+FxChunkPlan fx_rollout_plan(const FxKernelParams& P, int n_steps) {
   const char* fe = getenv("FXENV_CHUNK");  // read per launch: tests switch it between batches
   const int forced = fe ? atoi(fe) : 0;
+  const long long warps = (long long)fx_rollout_blocks(P) * FX_WARPS;
+  const long long N = P.cfg.num_envs;
   int chunk;
   if (forced > 0) chunk = forced;
-  else {
-    const long long warps = (long long)fx_rollout_blocks(P) * FX_WARPS;
-    const long long N = P.cfg.num_envs;
-    if (N <= warps) chunk = n_steps;
-    else { chunk = (int)((N * (long long)n_steps) / (warps * 6)); if (chunk > 64) chunk = 64; }
-  }
+  else if (N <= warps) chunk = n_steps;
+  else { chunk = (int)((N * (long long)n_steps) / (warps * 6)); if (chunk > 64) chunk = 64; }
   if (chunk < 1) chunk = 1;
   if (chunk > n_steps) chunk = n_steps;
-  return chunk;
+  FxChunkPlan pl = {};
+  pl.chunk = chunk;
+  pl.n_uniform = n_steps / chunk;
+  pl.n_rounds = pl.n_uniform;
+  pl.tail_start[0] = pl.n_uniform * chunk;
+  if (pl.tail_start[0] < n_steps) { pl.tail_start[1] = n_steps; pl.n_rounds++; }  // the remainder: one shorter round
+  return pl;
 }
 
 // seq_base / ticket_base: the values seq[] and the ticket counter hold when this launch starts (see fx_rollout_kernel);
 // reset_words: zero them first with a stream-ordered memset (then both bases must be 0) -- used inside stream captures,
 // where the host cannot track what the counters will hold at replay time.
 cudaError_t fx_launch_rollout(const FxKernelParams& P, const void* actions, float* obs, int obs_slots, float* reward,
-                              uint8_t* terminated, int n_steps, int chunk, unsigned seq_base, unsigned ticket_base,
+                              uint8_t* terminated, const FxChunkPlan& plan, unsigned seq_base, unsigned ticket_base,
                               bool reset_words, cudaStream_t stream) {
   const int N = P.cfg.num_envs;
   if (reset_words) {
@@ -1337,7 +1346,7 @@ cudaError_t fx_launch_rollout(const FxKernelParams& P, const void* actions, floa
   lc.attrs = at;
   lc.numAttrs = (reset_words || (P.debug & 4)) ? 0 : 1;  // behind a memset node: plain stream order
   return cudaLaunchKernelEx(&lc, pick_rollout(P), P, reinterpret_cast<const char*>(actions), obs, obs_slots, reward,
-                            terminated, n_steps, chunk, seq_base, ticket_base);
+                            terminated, plan, seq_base, ticket_base);
 }
 
 cudaError_t fx_launch_reset(const FxKernelParams& P, const int64_t* start_bar, const uint8_t* mask, int first,

@@ -41,6 +41,14 @@ struct FxDeviceState {
 
 #define FX_NSTAMP 12
 
+// How fx_rollout_kernel cuts the steps [0, n_steps) of a batch into rounds (one ticket = one env for the steps of one
+// round): n_uniform rounds of `chunk` steps, then rounds [tail_start[i], tail_start[i + 1]); n_rounds in total.
+#define FX_PLAN_TAIL 7
+struct FxChunkPlan {
+  int32_t chunk, n_uniform, n_rounds;
+  int32_t tail_start[FX_PLAN_TAIL + 1];
+};
+
 struct FxKernelParams {
   FxConfig cfg;
   FxPairTable pair[FXENV_MAX_PAIRS];
@@ -88,7 +96,7 @@ cudaError_t fx_launch_stats(const FxConfig& cfg, const double* candles, double* 
 cudaError_t fx_configure_kernels(FxKernelParams& P);
 bool fx_config_is_lean(const FxKernelParams& P);
 cudaError_t fx_launch_rollout(const FxKernelParams& P, const void* actions, float* obs, int obs_slots, float* reward,
-                              uint8_t* terminated, int n_steps, int chunk, unsigned seq_base, unsigned ticket_base,
+                              uint8_t* terminated, const FxChunkPlan& plan, unsigned seq_base, unsigned ticket_base,
                               bool reset_words, cudaStream_t stream);
 int fx_rollout_blocks(const FxKernelParams& P);
-int fx_rollout_chunk(const FxKernelParams& P, int n_steps);  // steps per ticket (the host's ticket accounting needs it)
+FxChunkPlan fx_rollout_plan(const FxKernelParams& P, int n_steps);  // the host's ticket accounting needs n_rounds
