@@ -40,13 +40,28 @@ namespace {
 // per-warp shared memory: the TMA-staged candle window + z-score statistics (+ the Sharpe ring) + one mbarrier
 struct WarpSmem {
   double *win, *stat, *ring;  // stat: [F][2] = {mean, 1/std} per feature (the layout of the per-bar statistics table)
+  double* carry;              // FX_CARRY_*: the env's scalar state between two steps run by the same warp (fx_rollout_kernel)
   unsigned long long* bar;
+};
+
+// Carry record (8-byte slots): what the next env-step loads in its first round trip.  A warp that keeps an env for several
+// consecutive steps (a ticket of fx_rollout_kernel) reads it here instead of from the state arrays in global memory --
+// which are still written every step -- and so starts its broker pass one L2 round trip earlier.
+enum {
+  FX_CARRY_CASH = 0, FX_CARRY_PSIZE, FX_CARRY_PPRICE, FX_CARRY_EQUITY, FX_CARRY_COMM, FX_CARRY_SUBNEED,
+  FX_CARRY_NBAR,                       // 5 slots: o, h, l, c, price column of the candle the next step works on
+  FX_CARRY_FLAGS_T = FX_CARRY_NBAR + 5, // int2 {flags, t}
+  FX_CARRY_BARS_N,                     // int2 {total_bars, n_orders}
+  FX_CARRY_NACC_TRADES,                // int2 {n_acc, trades}
+  FX_CARRY_START,                      // int64
+  FX_CARRY_RSTATS,                     // FX_RS_N slots
+  FX_CARRY_N = FX_CARRY_RSTATS + FX_RS_N
 };
 
 __host__ __device__ inline int fx_window_doubles(int W, int C) { return (W * C + 2 + 1) & ~1; }  // +1 alignment, even
 
 __host__ __device__ inline size_t fx_warp_smem_bytes(int win_doubles, int ring_len) {
-  size_t b = (size_t)win_doubles * 8 + 2 * FXENV_MAX_FEATURES * 8 + (size_t)ring_len * 8 + 16;
+  size_t b = (size_t)win_doubles * 8 + 2 * FXENV_MAX_FEATURES * 8 + (size_t)ring_len * 8 + FX_CARRY_N * 8 + 16;
   return (b + 15) & ~(size_t)15;
 }
 
@@ -56,6 +71,7 @@ __device__ __forceinline__ WarpSmem fx_carve(unsigned char* base, int win_double
   w.win = d; d += win_doubles;
   w.stat = d; d += 2 * FXENV_MAX_FEATURES;
   w.ring = d; d += ring_len;
+  w.carry = d; d += FX_CARRY_N;
   w.bar = reinterpret_cast<unsigned long long*>(d);
   return w;
 }
@@ -556,12 +572,15 @@ __device__ __forceinline__ uint32_t fx_apply_op(uint32_t m, uint32_t op) {
 }
 
 // One env-step of one env by one warp (everything between the cross-kernel dependency wait and the release).
-template <int STRAT, int REWARD, bool FAST5, bool O16, bool LEAN>
-__device__ __forceinline__ void fx_step_env(const FxKernelParams& P, const void* __restrict__ actions, float* __restrict__ obs,
+// CARRY (fx_rollout_kernel): the step leaves the env's scalar state in ws.carry and returns true if that record is valid;
+// carry_in = the previous call of this warp was the same env's previous step and returned true.
+template <int STRAT, int REWARD, bool FAST5, bool O16, bool LEAN, bool CARRY = false>
+__device__ __forceinline__ bool fx_step_env(const FxKernelParams& P, const void* __restrict__ actions, float* __restrict__ obs,
                                             float* __restrict__ reward, double* __restrict__ reward64,
                                             uint8_t* __restrict__ terminated, const int env, const int lane, const WarpSmem& ws,
                                             const unsigned phase = 0u, const unsigned step_row = 0u, const unsigned obs_slot_row = 0u,
-                                            uint16_t* __restrict__ obs16 = nullptr, const int stride16 = 0) {
+                                            uint16_t* __restrict__ obs16 = nullptr, const int stride16 = 0,
+                                            const bool carry_in = false) {
   // `actions` / `reward` / `terminated` / `obs` are the BASES of the caller's arrays (kernel parameters: they cost no
   // registers); this env-step's element is at index step_row + env (step_row = step * num_envs) and its observation row
   // at obs_slot_row + env (obs_slot_row = slot * num_envs).  Addresses are formed where they are used.
@@ -590,26 +609,53 @@ __device__ __forceinline__ void fx_step_env(const FxKernelParams& P, const void*
   FX_STAMP_GLOBAL(10);
 
   // ---- round trip 1: one batch of independent state loads (invariants: see FxDeviceState)
-  uint32_t flags = st.flags[env];
-  int32_t t = st.t[env];
-  int32_t total_bars = st.total_bars[env];
-  const int64_t start = st.start[env];
-  const int n = st.n_orders[env];
-  const int n_acc = st.n_acc[env];
-  const double sub_need = st.sub_need[env];
+  uint32_t flags;
+  int32_t t, total_bars;
+  int64_t start;
+  int n, n_acc;
+  double sub_need;
   FxEnvRegs e;
-  e.cash = st.cash[env]; e.psize = st.psize[env]; e.pprice = st.pprice[env]; e.equity = st.equity[env];
-  e.commission_paid = st.commission_paid[env]; e.trades = st.trades[env];
+  double2 nb_oh, nb_lc;
+  double nb_price, rsv = 0.0;
+  if (CARRY && carry_in) {  // the record this warp left behind one step ago (shared memory: broadcast reads)
+    const double* __restrict__ cr = ws.carry;
+    const int2 ft = *reinterpret_cast<const int2*>(cr + FX_CARRY_FLAGS_T);
+    const int2 bn = *reinterpret_cast<const int2*>(cr + FX_CARRY_BARS_N);
+    const int2 at = *reinterpret_cast<const int2*>(cr + FX_CARRY_NACC_TRADES);
+    flags = (uint32_t)ft.x; t = ft.y; total_bars = bn.x; n = bn.y; n_acc = at.x; e.trades = at.y;
+    start = *reinterpret_cast<const long long*>(cr + FX_CARRY_START);
+    sub_need = cr[FX_CARRY_SUBNEED];
+    e.cash = cr[FX_CARRY_CASH]; e.psize = cr[FX_CARRY_PSIZE]; e.pprice = cr[FX_CARRY_PPRICE]; e.equity = cr[FX_CARRY_EQUITY];
+    e.commission_paid = cr[FX_CARRY_COMM];
+    nb_oh.x = cr[FX_CARRY_NBAR]; nb_oh.y = cr[FX_CARRY_NBAR + 1]; nb_lc.x = cr[FX_CARRY_NBAR + 2]; nb_lc.y = cr[FX_CARRY_NBAR + 3];
+    nb_price = cr[FX_CARRY_NBAR + 4];
+#ifndef FX_NO_RUN_STATS
+    if (lane < FX_RS_N) rsv = cr[FX_CARRY_RSTATS + lane];
+#endif
+  } else {
+    flags = st.flags[env];
+    t = st.t[env];
+    total_bars = st.total_bars[env];
+    start = st.start[env];
+    n = st.n_orders[env];
+    n_acc = st.n_acc[env];
+    sub_need = st.sub_need[env];
+    e.cash = st.cash[env]; e.psize = st.psize[env]; e.pprice = st.pprice[env]; e.equity = st.equity[env];
+    e.commission_paid = st.commission_paid[env]; e.trades = st.trades[env];
+    // the candle this call works on was saved by the previous call (FxDeviceState::nbar): it travels in this same round trip
+    const double2* __restrict__ nb2 = reinterpret_cast<const double2*>(st.nbar + (int64_t)env * 6);
+    nb_oh = nb2[0]; nb_lc = nb2[1];
+    nb_price = st.nbar[(int64_t)env * 6 + 4];
+#ifndef FX_NO_RUN_STATS
+    if (lane < FX_RS_N) rsv = st.rstats[(int64_t)env * FX_RS_N + lane];  // DrawDown / TradeAnalyzer / SQN state
+#endif
+  }
   e.value = e.equity;
   int action_raw_i = 0;
   float action_raw_f = 0.0f;
   if (!LEAN && c.action_mode == FX_ACTION_CONTINUOUS) action_raw_f = reinterpret_cast<const float*>(actions)[FX_OUT_IDX()];
   else action_raw_i = reinterpret_cast<const int32_t*>(actions)[FX_OUT_IDX()];
-  // the candle this call works on was saved by the previous call (FxDeviceState::nbar), and the first 32 orders of
-  // the table sit at an address that only depends on the env: both travel in this same round trip
-  const double2* __restrict__ nb2 = reinterpret_cast<const double2*>(st.nbar + (int64_t)env * 6);
-  const double2 nb_oh = nb2[0], nb_lc = nb2[1];
-  const double nb_price = st.nbar[(int64_t)env * 6 + 4];
+  // the first 32 orders of the table sit at an address that only depends on the env: they travel with the state
   const int64_t obase = (int64_t)env * capP;
   uint32_t* __restrict__ gmeta = st.o_meta + obase;
   double* __restrict__ gp0 = st.o_p0 + obase;
@@ -618,7 +664,6 @@ __device__ __forceinline__ void fx_step_env(const FxKernelParams& P, const void*
   uint32_t pm0 = gmeta[lane];
   double pp0 = gp0[lane], pp1 = gp1[lane], psz = gsz[lane];
 #ifndef FX_NO_RUN_STATS
-  double rsv = (lane < FX_RS_N) ? st.rstats[(int64_t)env * FX_RS_N + lane] : 0.0;  // DrawDown / TradeAnalyzer / SQN state
   const FxRunStatsWarp rs{rsv, lane};
 #else   // A/B timing builds only
   const FxRunStatsNone rs;
@@ -672,7 +717,7 @@ __device__ __forceinline__ void fx_step_env(const FxKernelParams& P, const void*
       fx_window_wait(ws, phase);
       fx_emit_windows<FAST5, O16, LEAN>(P, lane, s, scale, ws.win + shift, ws.stat, FX_OBS_ROW(), FX_OBS_ROW16());
     }
-    return;
+    return false;  // (the carry record does not follow resets / ended episodes: the next step reloads the arrays)
   }
 
   // ---- step <-> bar timeline: the first step does not advance; later steps advance or exhaust
@@ -949,6 +994,15 @@ __device__ __forceinline__ void fx_step_env(const FxKernelParams& P, const void*
       if (reward64) reward64[FX_OUT_IDX()] = r;
       terminated[FX_OUT_IDX()] = term ? 1 : 0;
       fx_write_scalars<LEAN>(P, e, total_bars, last_price, FX_OBS_ROW(), FX_OBS_ROW16());
+      if (CARRY) {  // what the env's next step starts from, should this warp run it (the arrays above stay authoritative)
+        double* __restrict__ cr = ws.carry;
+        cr[FX_CARRY_CASH] = e.cash; cr[FX_CARRY_PSIZE] = e.psize; cr[FX_CARRY_PPRICE] = e.pprice; cr[FX_CARRY_EQUITY] = e.equity;
+        cr[FX_CARRY_COMM] = e.commission_paid; cr[FX_CARRY_SUBNEED] = sub_need_new;
+        *reinterpret_cast<int2*>(cr + FX_CARRY_FLAGS_T) = make_int2((int)e.flags, t);
+        *reinterpret_cast<int2*>(cr + FX_CARRY_BARS_N) = make_int2(total_bars, n_final);
+        *reinterpret_cast<int2*>(cr + FX_CARRY_NACC_TRADES) = make_int2(n_acc_new, e.trades);
+        *reinterpret_cast<long long*>(cr + FX_CARRY_START) = start;
+      }
     }
   } else {  // timing experiment only (FXENV_DEBUG & 2): cursor only
     if (lane == 0) { st.t[env] = t; st.flags[env] = flags; st.bar_index[env] = t + 1; reward[FX_OUT_IDX()] = 0.f; terminated[FX_OUT_IDX()] = 0; }
@@ -962,6 +1016,12 @@ __device__ __forceinline__ void fx_step_env(const FxKernelParams& P, const void*
   FX_EMIT_OBSERVATION();
 #endif
   if (lane < 5 && !(dbg & 2)) st.nbar[(int64_t)env * 6 + lane] = nbar_next;
+  if (CARRY) {
+    if (lane < 5) ws.carry[FX_CARRY_NBAR + lane] = nbar_next;
+#ifndef FX_NO_RUN_STATS
+    if (lane < FX_RS_N) ws.carry[FX_CARRY_RSTATS + lane] = rsv;
+#endif
+  }
   FX_STAMP(9);
   FX_STAMP_GLOBAL(11);
 #undef FX_EMIT_OBSERVATION
@@ -971,6 +1031,7 @@ __device__ __forceinline__ void fx_step_env(const FxKernelParams& P, const void*
 #undef FX_STAMP
 #undef FX_STAMP_DEP
 #undef FX_STAMP_GLOBAL
+  return CARRY && !(dbg & 2);
 }
 
 __device__ __forceinline__ int fx_ld_acquire(const int32_t* p) {
@@ -1063,13 +1124,17 @@ fx_rollout_kernel(const __grid_constant__ FxKernelParams P, const char* __restri
     }
     // the warp keeps the env for `chunk` consecutive steps: between them the state goes through memory as always, but
     // within one warp (__syncwarp orders it) -- no fence, no sequence word, no acquire round trip
+    bool carry = false;  // ws.carry holds this env's state as of step k (the warp ran step k - 1 itself)
+    unsigned slot_row = (k % (unsigned)obs_slots) * N;  // row offset of step k's slot in the observation ring
 #pragma unroll 1
     for (; k < k_end; ++k) {
 #if defined(FXENV_ENABLE_TIMING) || defined(FXENV_ENABLE_TIMELINE)
       if (P.timeline && lane == 0) { long long g__; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g__)); P.timeline[((size_t)k * N + env) * 2] = g__; }
 #endif
-      fx_step_env<STRAT, REWARD, FAST5, false, LEAN>(P, actions, obs, reward, nullptr, terminated, (int)env, lane, ws, phase, k * N,
-                                        (k % (unsigned)obs_slots) * N);
+      carry = fx_step_env<STRAT, REWARD, FAST5, false, LEAN, true>(P, actions, obs, reward, nullptr, terminated, (int)env, lane, ws,
+                                                                 phase, k * N, slot_row, nullptr, 0, carry);
+      slot_row += N;
+      if (slot_row == (unsigned)obs_slots * N) slot_row = 0u;
       __syncwarp();
       phase++;
 #if defined(FXENV_ENABLE_TIMING) || defined(FXENV_ENABLE_TIMELINE)
