@@ -350,15 +350,16 @@ __device__ __noinline__ void fx_emit_windows_t(const FxKernelParams& P, int lane
 // difference is far below half a float32 ulp).  prices | returns: a lane owns 4 consecutive rows.
 // PAD: the episode is younger than the window (s < W rows staged): output row w shows staged row max(0, w - pad), i.e. the
 // first row repeated `pad` times (feature_window_preprocessor.py:153-160,197-204) -- the first W steps of every episode.
-template <bool CLIP, bool TAME, bool O16, bool PAD, bool LONG>
-__device__ __noinline__ void fx_emit_fast5_q(const FxKernelParams& P, int lane, bool scale, const double* __restrict__ win,
+// Not inlined (one copy per kernel, several call sites); what it needs of the configuration arrives BY VALUE: through a
+// reference to the kernel parameters the callee would read them with generic loads (a constant-bank address formed at
+// run time), ~10 dependent round trips at the top of every row.  NOBIN: no binary pass-through feature (LEAN contract).
+template <bool CLIP, bool TAME, bool O16, bool PAD, bool LONG, bool NOBIN>
+__device__ __noinline__ void fx_emit_fast5_q(const int lane, const bool scale, const double* __restrict__ win,
                                              const double* sstat, float* __restrict__ out, uint16_t* __restrict__ o16_,
-                                             const int pad) {
+                                             const int pad, const int W, const float clipf, const int pc,
+                                             const unsigned binary_mask) {
   uint16_t* __restrict__ const o16 = O16 ? o16_ : nullptr;
-  const FxConfig& c = P.cfg;
-  const int W = c.window_size;
   const int pad5 = 5 * pad;
-  const float clipf = (float)c.feature_clip;
   if (lane < 30) {
     const int l5 = lane % 5;
     double r[4], a[4];
@@ -368,7 +369,7 @@ __device__ __noinline__ void fx_emit_fast5_q(const FxKernelParams& P, int lane, 
       int f = i - l5;                      // (4 * l5 + i) % 5, with 4 = -1 (mod 5)
       if (f < 0) f += 5;
       fi[i] = f;
-      const bool z = scale && (!P.any_binary || !c.feature_binary[f]);
+      const bool z = scale && (NOBIN || !((binary_mask >> f) & 1u));
       const double2 mr = *reinterpret_cast<const double2*>(sstat + 2 * f);  // {mean, 1/std}
       r[i] = z ? mr.y : 1.0;
       a[i] = z ? -(mr.x * mr.y) : 0.0;
@@ -396,7 +397,6 @@ __device__ __noinline__ void fx_emit_fast5_q(const FxKernelParams& P, int lane, 
       fx_st16x4(o16, 4 * q, v);
     }
   }
-  const int pc = c.price_col;
   float* __restrict__ op = out + 5 * W;
 #pragma unroll 1
   for (int w0 = 4 * lane; w0 < W; w0 += 128) {
@@ -428,9 +428,11 @@ __device__ __forceinline__ void fx_emit_windows(const FxKernelParams& P, int lan
   const int pad = P.cfg.window_size - s;  // > 0: the first rows of the window repeat the episode's first bar
   if (LEAN) {  // window % 4 == 0, price window, clip > 0 and finite data are part of the LEAN contract
     if ((reinterpret_cast<uintptr_t>(out) & 15) == 0) {
-      if (pad > 0) fx_emit_fast5_q<true, true, O16, true, false>(P, lane, scale, win, sstat, out, o16, pad);
-      else if (P.cfg.window_size >= 384) fx_emit_fast5_q<true, true, O16, false, true>(P, lane, scale, win, sstat, out, o16, 0);
-      else fx_emit_fast5_q<true, true, O16, false, false>(P, lane, scale, win, sstat, out, o16, 0);
+      const int W = P.cfg.window_size, pc = P.cfg.price_col;
+      const float clipf = (float)P.cfg.feature_clip;
+      if (pad > 0) fx_emit_fast5_q<true, true, O16, true, false, true>(lane, scale, win, sstat, out, o16, pad, W, clipf, pc, 0u);
+      else if (W >= 384) fx_emit_fast5_q<true, true, O16, false, true, true>(lane, scale, win, sstat, out, o16, 0, W, clipf, pc, 0u);
+      else fx_emit_fast5_q<true, true, O16, false, false, true>(lane, scale, win, sstat, out, o16, 0, W, clipf, pc, 0u);
     } else {
       fx_emit_windows_t<true, true, true, false, O16>(P, lane, s, scale, win, sstat, out, o16);
     }
@@ -438,9 +440,16 @@ __device__ __forceinline__ void fx_emit_windows(const FxKernelParams& P, int lan
   }
   if (FAST5 && (P.cfg.window_size & 3) == 0 && P.cfg.include_price_window && P.cfg.feature_clip > 0.0 && P.tame_data &&
       (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
-    if (pad > 0) fx_emit_fast5_q<true, true, O16, true, false>(P, lane, scale, win, sstat, out, o16, pad);
-    else if (P.cfg.window_size >= 384) fx_emit_fast5_q<true, true, O16, false, true>(P, lane, scale, win, sstat, out, o16, 0);
-    else fx_emit_fast5_q<true, true, O16, false, false>(P, lane, scale, win, sstat, out, o16, 0);
+    const int W = P.cfg.window_size, pc = P.cfg.price_col;
+    const float clipf = (float)P.cfg.feature_clip;
+    unsigned bm = 0u;  // binary pass-through features keep their raw value
+    if (P.any_binary) {
+#pragma unroll
+      for (int f = 0; f < 5; f++) bm |= P.cfg.feature_binary[f] ? (1u << f) : 0u;
+    }
+    if (pad > 0) fx_emit_fast5_q<true, true, O16, true, false, false>(lane, scale, win, sstat, out, o16, pad, W, clipf, pc, bm);
+    else if (W >= 384) fx_emit_fast5_q<true, true, O16, false, true, false>(lane, scale, win, sstat, out, o16, 0, W, clipf, pc, bm);
+    else fx_emit_fast5_q<true, true, O16, false, false, false>(lane, scale, win, sstat, out, o16, 0, W, clipf, pc, bm);
     return;
   }
   const bool lng = P.cfg.window_size >= 384;
