@@ -617,14 +617,17 @@ int make_map(FxEnv* env, CUtensorMap* map, void* base, uint64_t rows, uint64_t c
 //   policy(group, t) -> step(group, t) -> policy(group, t + 1) -> ...
 // on its own stream (forked from / joined into the caller's stream; inside a capture this becomes parallel branches of
 // the graph).  While one group's 128-row policy tiles occupy a few SMs, the other groups' env steps use the rest of the
-// device, and a group of <= 1024 envs steps in a single wave instead of the two of a 4096-env launch.
+// device, and a group of ~2048 envs steps in a single wave instead of the two of a 4096-env launch.  More, smaller groups
+// do not pay: every group adds two kernel nodes per step to the graph, and a group's policy tiles need SMs of their own.
+// (Also measured without gain: step kernels of 16 envs per CTA, so that a group's step leaves whole SMs free.)
 cudaError_t enqueue_rollout(FxEnv* env, FxPolicy* pol, const FxRollout& io, cudaStream_t s) {
   const size_t N = (size_t)env->P.cfg.num_envs, D = (size_t)env->P.obs_dim;
   const int H = io.horizon, slots = io.obs_slots;
   cudaError_t e = fx_launch_observe(env->P, io.obs, s, pol->obs16[0], pol->k_pad);  // the current observation, both copies
   if (e != cudaSuccess) return e;
-  int groups = (int)(N / 1024);
+  int groups = (int)(N / 2048);  // measured at 4096 envs (cfg4 shape), us/step: 41.2 with 1 group, 37.7 with 2, 39.5 with 4
   if (groups > FxPolicy::kGroups) groups = FxPolicy::kGroups;
+  if (const char* ge = getenv("FXENV_ROLLOUT_GROUPS")) { const int g = atoi(ge); if (g >= 1 && g <= FxPolicy::kGroups) groups = g; }  // measurements
   if (groups < 1 || (env->P.debug & 64)) groups = 1;
   const size_t per = ((N + groups - 1) / groups + FX_POLICY_TILE_M - 1) / FX_POLICY_TILE_M * FX_POLICY_TILE_M;
   if (groups > 1) {

@@ -12,7 +12,8 @@ from gym_fx_b200.vec_env import VecFxEnv
 H = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 wl = sys.argv[3] if len(sys.argv) > 3 else "cfg4"
-cfg, candles, minutes, N, D, _, desc = bench.build_workload(wl)
+envs = int(sys.argv[4]) if len(sys.argv) > 4 else None
+cfg, candles, minutes, N, D, _, desc = bench.build_workload(wl, envs)
 env = VecFxEnv(cfg, candles, minutes)
 env.reset(torch.as_tensor(start_offsets(N, bench.T_BARS, 4000, 256)))
 torch.manual_seed(0)
