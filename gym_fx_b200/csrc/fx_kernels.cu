@@ -31,6 +31,13 @@
 #include "fx_kernels.cuh"
 
 #define FX_FULL 0xffffffffu
+#ifndef FX_LONG_UNROLL
+#define FX_LONG_UNROLL 2   // unroll factor of the 16-byte emit loop for long windows
+#endif
+#ifndef FX_LONG_MIN_W
+#define FX_LONG_MIN_W 384  // windows of at least this many rows use the unrolled loop
+#endif
+constexpr int kLongUnroll = FX_LONG_UNROLL;  // (a macro is not expanded inside #pragma unroll)
 #ifndef FX_EMIT_EARLY
 #define FX_EMIT_EARLY 0  // 1: emit the observation windows right after the order sweep (measured: 12.44 vs 12.05 us/step, worse)
 #endif
@@ -54,6 +61,8 @@ enum {
   FX_CARRY_BARS_N,                     // int2 {total_bars, n_orders}
   FX_CARRY_NACC_TRADES,                // int2 {n_acc, trades}
   FX_CARRY_START,                      // int64
+  FX_CARRY_SHARPE,                     // int2 {deque length, head}; the deque itself stays in WarpSmem::ring
+  FX_CARRY_SHARPE_LAST,                // int32 last step seen by the Sharpe plugin
   FX_CARRY_RSTATS,                     // FX_RS_N slots
   FX_CARRY_N = FX_CARRY_RSTATS + FX_RS_N
 };
@@ -378,7 +387,7 @@ __device__ __noinline__ void fx_emit_fast5_q(const int lane, const bool scale, c
     float4* __restrict__ o4 = reinterpret_cast<float4*>(out);
     // short windows: not unrolled -- the warps of an SM sit at different places of a large kernel, and the smaller loop
     // body is worth more in instruction-cache hits than the saved loop overhead; LONG (W >= 384): unrolled by 2
-#pragma unroll(LONG ? 2 : 1)
+#pragma unroll(LONG ? kLongUnroll : 1)
     for (int q = lane; q < nq; q += 30) {
       double x[4];
       if (PAD) {  // element j of the block comes from staged element j - 5 * pad, or from row 0 (same feature) in the pad
@@ -431,7 +440,7 @@ __device__ __forceinline__ void fx_emit_windows(const FxKernelParams& P, int lan
       const int W = P.cfg.window_size, pc = P.cfg.price_col;
       const float clipf = (float)P.cfg.feature_clip;
       if (pad > 0) fx_emit_fast5_q<true, true, O16, true, false, true>(lane, scale, win, sstat, out, o16, pad, W, clipf, pc, 0u);
-      else if (W >= 384) fx_emit_fast5_q<true, true, O16, false, true, true>(lane, scale, win, sstat, out, o16, 0, W, clipf, pc, 0u);
+      else if (W >= FX_LONG_MIN_W) fx_emit_fast5_q<true, true, O16, false, true, true>(lane, scale, win, sstat, out, o16, 0, W, clipf, pc, 0u);
       else fx_emit_fast5_q<true, true, O16, false, false, true>(lane, scale, win, sstat, out, o16, 0, W, clipf, pc, 0u);
     } else {
       fx_emit_windows_t<true, true, true, false, O16>(P, lane, s, scale, win, sstat, out, o16);
@@ -448,7 +457,7 @@ __device__ __forceinline__ void fx_emit_windows(const FxKernelParams& P, int lan
       for (int f = 0; f < 5; f++) bm |= P.cfg.feature_binary[f] ? (1u << f) : 0u;
     }
     if (pad > 0) fx_emit_fast5_q<true, true, O16, true, false, false>(lane, scale, win, sstat, out, o16, pad, W, clipf, pc, bm);
-    else if (W >= 384) fx_emit_fast5_q<true, true, O16, false, true, false>(lane, scale, win, sstat, out, o16, 0, W, clipf, pc, bm);
+    else if (W >= FX_LONG_MIN_W) fx_emit_fast5_q<true, true, O16, false, true, false>(lane, scale, win, sstat, out, o16, 0, W, clipf, pc, bm);
     else fx_emit_fast5_q<true, true, O16, false, false, false>(lane, scale, win, sstat, out, o16, 0, W, clipf, pc, bm);
     return;
   }
@@ -970,9 +979,16 @@ __device__ __forceinline__ bool fx_step_env(const FxKernelParams& P, const void*
       // deque of per-step returns: stage the ring in shared memory (coalesced), push, evaluate in Python order
       const int Wn = c.sharpe_window;
       double* gring = st.sh_ring + (int64_t)env * Wn;
-      int32_t len = st.sh_len[env], head = st.sh_head[env], last = st.sh_last_step[env];
-      for (int k = lane; k < Wn; k += 32) ws.ring[k] = gring[k];
-      __syncwarp();
+      int32_t len, head, last;
+      if (CARRY && carry_in) {  // this warp ran the env's previous step: its copy of the deque is current
+        const int2 lh = *reinterpret_cast<const int2*>(ws.carry + FX_CARRY_SHARPE);
+        len = lh.x; head = lh.y;
+        last = *reinterpret_cast<const int32_t*>(ws.carry + FX_CARRY_SHARPE_LAST);
+      } else {
+        len = st.sh_len[env]; head = st.sh_head[env]; last = st.sh_last_step[env];
+        for (int k = lane; k < Wn; k += 32) ws.ring[k] = gring[k];
+        __syncwarp();
+      }
       const double ret = (e.equity - e.prev_equity) / c.reward_initial_cash;
       int slot;  // where the new return lands (same rule as fx_sharpe_push)
       if (e.bar_index <= last) slot = 0; else slot = (len == Wn) ? head : (head + len) % Wn;
@@ -982,6 +998,10 @@ __device__ __forceinline__ bool fx_step_env(const FxKernelParams& P, const void*
       if (lane == 0) {
         gring[slot] = ret;
         st.sh_len[env] = len; st.sh_head[env] = head; st.sh_last_step[env] = last;
+        if (CARRY) {
+          *reinterpret_cast<int2*>(ws.carry + FX_CARRY_SHARPE) = make_int2(len, head);
+          *reinterpret_cast<int32_t*>(ws.carry + FX_CARRY_SHARPE_LAST) = last;
+        }
       }
     }
     const bool term = ((e.flags & FX_FLAG_TERMINATED) != 0u) || (e.equity <= c.min_equity);  // app/env.py:157

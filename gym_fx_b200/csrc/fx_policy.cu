@@ -41,7 +41,7 @@ constexpr int kThreads = 192;                         // warp 0 TMA, warp 1 MMA,
 constexpr uint32_t kTmemCols = 512;
 
 struct __align__(8) Barriers {
-  unsigned long long full[kStages], empty[kStages], d1_full, h1_ready, d2_full;
+  unsigned long long full[kStages], empty[kStages], d1_full, h1_ready[kHidden / kBlockK], d2_full;
   uint32_t tmem_base;
 };
 
@@ -146,7 +146,8 @@ fx_policy_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_const
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w1) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w2) : "memory");
     for (int s = 0; s < kStages; s++) { mbar_init(&bar->full[s], 1); mbar_init(&bar->empty[s], 1); }
-    mbar_init(&bar->d1_full, 1); mbar_init(&bar->h1_ready, 128); mbar_init(&bar->d2_full, 1);
+    mbar_init(&bar->d1_full, 1); mbar_init(&bar->d2_full, 1);
+    for (int j = 0; j < kHidden / kBlockK; j++) mbar_init(&bar->h1_ready[j], 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // one warp allocates (and later frees) the tensor memory: 512 columns = both accumulators
@@ -203,10 +204,11 @@ fx_policy_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_const
         umma_commit(&bar->empty[s]);
       }
       umma_commit(&bar->d1_full);  // arrives when every layer-1 MMA has retired
-      mbar_wait(&bar->h1_ready, 0);  // the epilogue has written tanh(D1 + b1) as the bf16 A operand
-      tc_fence_after();
       for (int j = 0; j < kb2; j++) {
         const int it = k_blocks1 + j, s = it % kStages;
+        // k-block j of layer 2 = columns [64 j, 64 j + 64) of h1: it starts as soon as the epilogue has written those
+        // (tanh(D1 + b1) as the bf16 A operand), while the epilogue is still working on the later columns of D1
+        mbar_wait(&bar->h1_ready[j], 0);
         mbar_wait(&bar->full[s], (it / kStages) & 1);
         tc_fence_after();
         const uint32_t a = smem_u32(smem + kOffH1 + j * kABytes), b = smem_u32(smem + s * kStageBytes) + kABytes;
@@ -246,10 +248,12 @@ fx_policy_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_const
         const int chunk = ((c & 1) * 4 + j) ^ (row & 7);
         *reinterpret_cast<uint4*>(rowp + chunk * 16) = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
       }
+      if (c & 1) {  // this row's 64 columns of k-block c / 2 are complete
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core
+        tc_fence_before();
+        mbar_arrive(&bar->h1_ready[c >> 1]);
+      }
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core
-    tc_fence_before();
-    mbar_arrive(&bar->h1_ready);
 
     mbar_wait(&bar->d2_full, 0);
     tc_fence_after();
