@@ -1084,7 +1084,7 @@ template <int STRAT, int REWARD, bool FAST5, bool LEAN>
 __global__ void __launch_bounds__(FX_WARPS * 32, FX_MIN_BLOCKS)
 fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict__ actions, float* __restrict__ obs,
                float* __restrict__ reward, double* __restrict__ reward64, uint8_t* __restrict__ terminated,
-               const int env_begin, const int env_end, uint16_t* __restrict__ obs16, const int stride16) {
+               const int env_begin, const int env_end, uint16_t* __restrict__ obs16, const int stride16, const FxTileSync sync) {
   extern __shared__ __align__(16) unsigned char fx_smem[];
   const FxConfig& c = P.cfg;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1095,10 +1095,44 @@ fx_step_kernel(const __grid_constant__ FxKernelParams P, const void* __restrict_
   const WarpSmem ws = fx_carve(fx_smem + (size_t)warp * fx_warp_smem_bytes(win_doubles, ring_len), win_doubles, ring_len);
   asm volatile("griddepcontrol.launch_dependents;");
   fx_window_init(lane, ws);  // mbarrier init + fence
-  asm volatile("griddepcontrol.wait;" ::: "memory");
+#ifdef FXENV_ENABLE_TIMING  // kernel-chain probe (tools/chain_probe.py): CTA 0 logs {kind, entry, after the wait, exit}
+  long long* klog = nullptr;
+  if (P.timeline && blockIdx.x == 0 && lane == 0 && obs16) {
+    long long g0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
+    const unsigned long long seqno = atomicAdd(reinterpret_cast<unsigned long long*>(P.timeline), 1ull);
+    klog = P.timeline + 8 + (seqno % 1024ull) * 4;
+    klog[0] = 1; klog[1] = g0;
+  }
+#endif
+  if (sync.act_flag) {  // closed loop: this env's action is ready once the policy has published its 128-env tile
+    if (lane == 0) {
+      const int32_t* f = sync.act_flag + env / FX_SYNC_TILE;
+      int polls = 0;
+      while (fx_ld_acquire(f) < sync.epoch) {
+        if (++polls > FX_SYNC_MAX_POLLS) { atomicAdd(sync.timeouts, 1); break; }
+        __nanosleep(64);
+      }
+    }
+    __syncwarp();
+  } else {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+  }
+#ifdef FXENV_ENABLE_TIMING
+  if (klog) { long long g1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1)); klog[2] = g1; }
+#endif
   // the bf16 copy of the row (closed loop only) is a compile-time variant: no per-store pointer tests in the plain step
   if (obs16) fx_step_env<STRAT, REWARD, FAST5, true, LEAN>(P, actions, obs, reward, reward64, terminated, env, lane, ws, 0u, 0u, 0u, obs16, stride16);
   else fx_step_env<STRAT, REWARD, FAST5, false, LEAN>(P, actions, obs, reward, reward64, terminated, env, lane, ws);
+  if (sync.done_cnt) {  // this env's row (float32 and bf16) and state are complete: count it for its tile
+    __syncwarp();
+    if (lane == 0) {
+      asm volatile("fence.proxy.async;" ::: "memory");  // the policy kernel reads the bf16 rows through TMA (async proxy)
+      asm volatile("red.release.gpu.global.add.s32 [%0], 1;" :: "l"(sync.done_cnt + env / FX_SYNC_TILE) : "memory");
+    }
+  }
+#ifdef FXENV_ENABLE_TIMING
+  if (klog) { long long g2; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g2)); klog[3] = g2; }
+#endif
 }
 
 // ---- K steps in ONE launch (fxenv_step_many): persistent warps pull (step chunk, env) tickets ----------------------
@@ -1259,7 +1293,7 @@ __global__ void fx_stats_kernel(FxConfig c, const double* __restrict__ candles, 
   stats[idx * 2 + 1] = rc;
 }
 
-typedef void (*StepKernel)(const FxKernelParams, const void*, float*, float*, double*, uint8_t*, int, int, uint16_t*, int);
+typedef void (*StepKernel)(const FxKernelParams, const void*, float*, float*, double*, uint8_t*, int, int, uint16_t*, int, const FxTileSync);
 typedef void (*RolloutKernel)(const FxKernelParams, const char*, float*, int, float*, uint8_t*, const FxChunkPlan, unsigned, unsigned);
 
 // mode: 0 = general features, 1 = 5-feature fast path, 2 = LEAN (implies the 5-feature fast path)
@@ -1329,6 +1363,7 @@ cudaError_t fx_configure_kernels(FxKernelParams& P) {
   const size_t want = (size_t)FX_MIN_BLOCKS * (smem + 1024);
   int pct = (int)((want * 100 + 228 * 1024 - 1) / (228 * 1024));
   if (pct > 100) pct = 100;
+  if (const char* cv = getenv("FXENV_CARVEOUT")) { const int v = atoi(cv); if (v >= pct && v <= 100) pct = v; }  // measurements
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1369,7 +1404,8 @@ bool fx_config_is_lean(const FxKernelParams& P) {
 }
 
 cudaError_t fx_launch_step(const FxKernelParams& P, const void* actions, float* obs, float* reward, double* reward64,
-                           uint8_t* terminated, cudaStream_t stream, int env_begin, int env_end, uint16_t* obs16, int stride16) {
+                           uint8_t* terminated, cudaStream_t stream, int env_begin, int env_end, uint16_t* obs16, int stride16,
+                           const FxTileSync* sync) {
   if (env_end < 0) env_end = P.cfg.num_envs;
   cudaLaunchConfig_t lc = {};
   lc.gridDim = dim3((env_end - env_begin + FX_WARPS - 1) / FX_WARPS);
@@ -1381,7 +1417,9 @@ cudaError_t fx_launch_step(const FxKernelParams& P, const void* actions, float* 
   at[0].val.programmaticStreamSerializationAllowed = 1;
   lc.attrs = at;
   lc.numAttrs = (P.debug & 4) ? 0 : 1;  // FXENV_DEBUG & 4: plain stream-serialised launches (A/B timing only)
-  return cudaLaunchKernelEx(&lc, pick_kernel(P), P, actions, obs, reward, reward64, terminated, env_begin, env_end, obs16, stride16);
+  const FxTileSync no_sync = {nullptr, nullptr, nullptr, 0};
+  return cudaLaunchKernelEx(&lc, pick_kernel(P), P, actions, obs, reward, reward64, terminated, env_begin, env_end, obs16, stride16,
+                            sync ? *sync : no_sync);
 }
 
 int fx_rollout_blocks(const FxKernelParams& P) {

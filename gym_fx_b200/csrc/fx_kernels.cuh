@@ -85,9 +85,25 @@ struct FxKernelParams {
 
 // host-callable launchers (fx_kernels.cu)
 // one step of the envs [env_begin, env_end) (env_end < 0: all); the array arguments are the bases for env 0
+// Fine-grained hand-over between the policy kernel and the env-step kernel of a closed-loop rollout (fxenv_rollout), per
+// 128-env tile, instead of whole-kernel dependencies: the step kernel of step t starts an env as soon as the policy has
+// published the tile's actions (act_flag[tile] >= t + 1), and the policy kernel of step t + 1 starts a tile as soon as
+// its envs have finished step t (done_cnt[tile] == envs of the tile x (t + 1)).  Both kernels are launched with the
+// programmatic-dependent-launch attribute and are resident together; a dependent grid is only launched once every CTA
+// of its predecessor has started, so whoever is waited for is always running.  nullptr members: plain kernel order.
+struct FxTileSync {
+  int32_t* act_flag;   // [tiles] written by the policy kernel (release), polled by the step kernel (acquire)
+  int32_t* done_cnt;   // [tiles] incremented by the step kernel (release), polled by the policy kernel (acquire)
+  int32_t* timeouts;   // [1] number of polls that gave up (a bug or a lost launch: results are then invalid; tests assert 0)
+  int32_t epoch;       // t + 1
+};
+#define FX_SYNC_TILE 128
+#define FX_SYNC_MAX_POLLS (1 << 22)   // x ~64 ns: a poll gives up after ~0.3 s instead of hanging the device  // obs16: optional bf16 copy of the rows
+
 cudaError_t fx_launch_step(const FxKernelParams& P, const void* actions, float* obs, float* reward, double* reward64,
                            uint8_t* terminated, cudaStream_t stream, int env_begin = 0, int env_end = -1,
-                           uint16_t* obs16 = nullptr, int stride16 = 0);  // obs16: optional bf16 copy of the rows
+                           uint16_t* obs16 = nullptr, int stride16 = 0, const FxTileSync* sync = nullptr);
+
 cudaError_t fx_launch_reset(const FxKernelParams& P, const int64_t* start_bar, const uint8_t* mask, int first,
                             cudaStream_t stream);
 cudaError_t fx_launch_observe(const FxKernelParams& P, float* obs, cudaStream_t stream, uint16_t* obs16 = nullptr,

@@ -393,6 +393,13 @@ class FusedPolicy:
         if weights is not None:
             self.set_weights(weights)
 
+    def sync_timeouts(self) -> int:
+        """Polls of the last rollout's tile hand-over that gave up (0 unless something is broken); synchronises."""
+        rc = int(self.env.L.fxenv_policy_sync_timeouts(self._p))
+        if rc < 0:
+            _native.check(self.env.L, self.env._h, rc, "fxenv_policy_sync_timeouts")
+        return rc
+
     def set_weights(self, weights):
         if not isinstance(weights, dict):
             m = weights

@@ -282,6 +282,11 @@ int fxenv_policy_destroy(FxPolicy* pol);
 /* `horizon` closed-loop steps starting from the env's current state; everything is enqueued on `stream`
  * (2 * horizon + 2 kernels; the launch sequence is cached as a CUDA graph per buffer set). */
 int fxenv_rollout(FxEnv* env, FxPolicy* pol, const FxRollout* io, void* stream);
+/* Inside a rollout the policy kernel and the env-step kernel hand 128-env tiles to each other through flags in device
+ * memory instead of whole-kernel dependencies; a poll that is never answered gives up after ~0.3 s instead of hanging
+ * the device.  Returns how many polls of the LAST rollout gave up (0 unless something is broken; then that rollout's
+ * results are invalid), or <0.  Synchronises the device. */
+int fxenv_policy_sync_timeouts(FxPolicy* pol);
 
 #ifdef __cplusplus
 }

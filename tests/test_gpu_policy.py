@@ -53,8 +53,11 @@ def _ref_forward(net, obs, emulate_bf16):
     return logits, value
 
 
-@pytest.mark.parametrize("N,H", [(512, 6), (100, 4), (4096, 3)])
-def test_rollout_policy_matches_torch_reference_and_env_matches_single_steps(N, H):
+@pytest.mark.parametrize("N,H,tile_sync", [(512, 6, 0), (100, 4, 1), (4096, 3, 0), (4096, 5, 1)])
+def test_rollout_policy_matches_torch_reference_and_env_matches_single_steps(N, H, tile_sync, monkeypatch):
+    # tile_sync: the experimental per-tile hand-over between the policy and the step kernel (FXENV_TILE_SYNC, fx_kernels.cuh
+    # FxTileSync) must give the same results as plain kernel order
+    monkeypatch.setenv("FXENV_TILE_SYNC", str(tile_sync))
     torch.manual_seed(N)
     cfg, candles, minutes, make = _env(N)
     env, twin = make(), make()
@@ -72,6 +75,7 @@ def test_rollout_policy_matches_torch_reference_and_env_matches_single_steps(N, 
     gum = -torch.log(-torch.log(torch.rand((H, N, 3), device="cuda", generator=torch.Generator(device="cuda").manual_seed(2)).clamp(1e-9, 1 - 1e-9)))
     out = env.rollout(pol, H, gumbel=gum)
     torch.cuda.synchronize()
+    assert pol.sync_timeouts() == 0, "a tile hand-over between the policy and the step kernel was never answered"
     obs, act, logp, val, rew, done = (out[k] for k in ("obs", "actions", "logp", "value", "reward", "done"))
     assert obs.shape == (H + 1, N, env.obs_dim) and act.dtype == torch.int32
     # ---- env side: identical to single steps with the same actions
