@@ -462,10 +462,10 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.synchronize(dev)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     nfull = K // chunk
-    # the device spins ~50 us while the host enqueues the start event and the first launch: the timed region starts with
-    # the launch already queued, as it is for every launch after the first in a training loop (host launch latency is
-    # not device time of the K steps; without this a 20-step run carries ~10 us of it)
-    torch.cuda._sleep(100_000)
+    # the device spins ~0.3 ms while the host enqueues the start event and the launches: the timed region starts with
+    # the first launch already queued, as it is for every launch after the first in a training loop (host launch latency
+    # is not device time of the K steps; without this a 20-step run carries ~10 us of it, more when 8 ranks share a host)
+    torch.cuda._sleep(600_000)
     ev0.record(stream)
     for _ in range(nfull):
         full()
