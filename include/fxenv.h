@@ -209,8 +209,9 @@ int fxenv_step(FxEnv* env, const void* actions_dev, float* obs_dev, float* rewar
  * drivers: strategy_plugins/default_strategy.py:38-53, the loop of app/main.py:57-65); step k reads
  * actions_dev + k*num_envs and writes reward/terminated at k*num_envs; obs rows go to
  * obs_dev + (k % obs_slots)*num_envs*obs_dim (obs_slots >= 1).  Results are identical to n_steps calls of fxenv_step.
- * Two engines, chosen by size (fxenv_step_many_engine): 1 = one persistent launch whose warps pull (step, env) tickets
- * and honour per-env dependencies only; 0 = a CUDA graph of n_steps single-step launches, cached by pointer set. */
+ * Two engines (fxenv_step_many_engine): 1 = one persistent launch whose warps pull (round of consecutive steps, env)
+ * tickets and honour per-env dependencies only (every batch of more than one step); 0 = a CUDA graph of n_steps
+ * single-step launches, cached by pointer set. */
 int fxenv_step_many(FxEnv* env, int n_steps, const void* actions_dev, float* obs_dev, int obs_slots,
                     float* reward_dev, uint8_t* terminated_dev, void* stream);
 
