@@ -263,8 +263,18 @@ def test_step_many_graph_and_step_host_match_step(cfg2_full):
         h_act.copy_(acts[k])
         c_env.step_host(h_act, h_obs, h_rew, h_term)
         assert torch.equal(rew, rews[k]) and torch.equal(term.to(torch.uint8), terms[k])
-        assert torch.equal(rew.cpu(), h_rew) and torch.equal(obs.cpu(), h_obs)
+        assert torch.equal(rew.cpu(), h_rew) and torch.equal(obs.cpu(), h_obs) and torch.equal(term.to(torch.uint8).cpu(), h_term)
     assert torch.equal(obs, ring[(K - 1) % 2])
+    # pageable host buffers (not pinned) take the same path through staged copies: same results
+    p_act, p_obs = torch.empty(N, dtype=torch.int32), torch.empty((N, D), dtype=torch.float32)
+    p_rew, p_term = torch.empty(N, dtype=torch.float32), torch.empty(N, dtype=torch.uint8)
+    for k in range(3):
+        obs, rew, term, _, _ = a_env.step(acts[k])
+        p_act.copy_(acts[k])
+        c_env.step_host(p_act, p_obs, p_rew, p_term)
+        assert torch.equal(rew.cpu(), p_rew) and torch.equal(obs.cpu(), p_obs) and torch.equal(term.to(torch.uint8).cpu(), p_term)
+    b_env.step_many(acts[:3], ring, rews[:3], terms[:3])   # keep the twin in step for the comparisons below
+    torch.cuda.synchronize()
     assert torch.equal(a_env.info()["equity"], b_env.info()["equity"])
     summ = a_env.summary()
     assert torch.equal(summ["final_equity"], a_env.info()["equity"]) and summ["order_overflow_envs"] == 0
