@@ -346,7 +346,7 @@ def closed_loop_block(K, rank, world, dev, dist):
 
     cfg, candles, minutes, N, D, _, desc = build_workload("cfg4")
     env = VecFxEnv(cfg, candles, minutes, device=dev)
-    H = max(2, min(32, K))
+    H = 32 if K >= 8 else max(2, K)                          # rollout horizon (not tied to --steps: a PPO-sized chunk)
     reps = max(1, min(8, K // H))
     pre = preroll_steps(cfg)
     env.reset(torch.as_tensor(shard_starts(N, rank, world, T_BARS, (reps + 3) * H + pre + 128, 256)))

@@ -425,6 +425,40 @@ def test_step_many_edge_sizes_match_single_steps(N, K):
     many.close(); single.close()
 
 
+def test_misaligned_observation_buffers_take_the_general_emitter():
+    """The 16-byte-store row emitter needs 16-byte aligned observation rows; a caller's buffer that starts on an odd float
+    (a view into a larger allocation) must still work: such rows go through the general emitter.  Rewards, done flags and
+    state are identical; the rows agree within the observation tolerance (the fast emitter evaluates a z-score as one
+    fma), for single steps and for the persistent batch launch."""
+    from gym_fx_b200.vec_env import VecFxEnv
+    cfgd, plugins, kw = VEC_CASES["cfg2_fixed_fw128_pnl"]
+    N, T, K = 300, 3000, 9
+    cfg, candles, minutes = _mk(cfgd, plugins, N, T=T, order_capacity=256, **kw)
+    starts = torch.as_tensor(start_offsets(N, T, 100, 300))
+    acts = torch.randint(0, 3, (K, N), dtype=torch.int32, generator=torch.Generator().manual_seed(5)).cuda()
+    a, b = VecFxEnv(cfg, candles, minutes), VecFxEnv(cfg, candles, minutes)
+    a.reset(starts); b.reset(starts)
+    D = a.obs_dim
+    odd = torch.zeros(N * D + 1, dtype=torch.float32, device="cuda")[1:].view(N, D)     # base pointer = 4 (mod 16)
+    assert odd.data_ptr() % 16 == 4
+    for k in range(3):
+        oa, ra, ta, _, _ = a.step(acts[k])
+        ob, rb, tb, _, _ = b.step(acts[k], out_obs=odd)
+        assert torch.equal(ra, rb) and torch.equal(ta, tb)
+        np.testing.assert_allclose(odd.cpu().numpy(), oa.cpu().numpy(), rtol=1e-5, atol=2e-6)
+    ring_a = torch.zeros((2, N, D), dtype=torch.float32, device="cuda")
+    ring_b = torch.zeros(2 * N * D + 1, dtype=torch.float32, device="cuda")[1:].view(2, N, D)
+    rews = torch.zeros((2, K, N), dtype=torch.float32, device="cuda")
+    terms = torch.zeros((2, K, N), dtype=torch.uint8, device="cuda")
+    a.step_many(acts, ring_a, rews[0], terms[0])
+    b.step_many(acts, ring_b, rews[1], terms[1])
+    torch.cuda.synchronize()
+    assert torch.equal(rews[0], rews[1]) and torch.equal(terms[0], terms[1])
+    np.testing.assert_allclose(ring_b.cpu().numpy(), ring_a.cpu().numpy(), rtol=1e-5, atol=2e-6)
+    assert bytes(a.get_state()) == bytes(b.get_state())
+    a.close(); b.close()
+
+
 @pytest.mark.parametrize("chunk", [1, 3, 7, 64])
 def test_step_many_ticket_chunk_lengths_agree(chunk):
     """fx_rollout_kernel hands a warp `chunk` consecutive steps of an env per ticket (fx_rollout_chunk; FXENV_CHUNK forces
