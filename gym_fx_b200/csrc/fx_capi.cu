@@ -556,6 +556,22 @@ int fxenv_debug_timeline(FxEnv* env, long long* out_host) {
   return env->timeline_steps;
 }
 
+/* debug / tests (pure host arithmetic, no CUDA call): how fxenv_step_many would cut n_steps into ticket rounds for
+ * num_envs envs on a device holding resident_warps warps of the rollout kernel.  starts[0..rounds] receives the first
+ * step of every round (starts[rounds] = n_steps); returns the number of rounds, or <0 if `cap` entries are not enough. */
+int fxenv_debug_rollout_plan(int num_envs, int resident_warps, int n_steps, int* starts, int cap) {
+  if (num_envs < 1 || resident_warps < 1 || n_steps < 1 || !starts) return FXENV_E_INVALID;
+  FxKernelParams P = {};
+  P.cfg.num_envs = num_envs;
+  P.resident_blocks = (resident_warps + FX_WARPS - 1) / FX_WARPS;
+  const FxChunkPlan pl = fx_rollout_plan(P, n_steps);
+  if (pl.n_rounds + 1 > cap) return FXENV_E_INVALID;
+  int r = 0;
+  for (; r < pl.n_uniform; r++) starts[r] = r * pl.chunk;
+  for (int t = 0; r <= pl.n_rounds; r++, t++) starts[r] = pl.tail_start[t];
+  return pl.n_rounds;
+}
+
 /* debug (FXENV_TIMING=1): copies the [num_envs][FX_NSTAMP] phase stamps of the last step; returns FX_NSTAMP or <0 */
 int fxenv_debug_timings(FxEnv* env, long long* out_host) {
   if (!env || !out_host || !env->P.timing) return FXENV_E_STATE;

@@ -160,3 +160,42 @@ def test_metrics_summary_matches_reference_golden_fields():
     from gym_fx_b200.metrics_plugins.default_metrics import Plugin
     s = Plugin().summarize(initial_cash=10000.0, final_equity=10000.095791583166, analyzers={}, config={})
     assert s["total_return"] == 9.579158316563863e-06 and s["trades_total"] == 0 and s["sharpe_ratio"] is None
+
+
+def test_rollout_ticket_plan_covers_every_step_once(monkeypatch):
+    """fx_rollout_plan (the rounds of a fxenv_step_many batch: one ticket = one env for the steps of one round) is pure host
+    arithmetic: the rounds partition [0, n_steps) in order, are at most 64 steps long, a batch whose envs all have a
+    resident warp is a single round (no hand-over), larger batches leave at least ~6 tickets per resident warp unless
+    the rounds are already single steps, and FXENV_CHUNK forces the length (remainder as a shorter last round)."""
+    import ctypes as C
+    from gym_fx_b200 import _native
+    L = _native.load()
+    f = L.fxenv_debug_rollout_plan
+    f.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int]
+    f.restype = C.c_int
+
+    def plan(n_envs, warps, steps):
+        buf = (C.c_int * 8192)()
+        n = f(n_envs, warps, steps, buf, 8192)
+        assert n >= 1
+        return list(buf[:n + 1])
+
+    monkeypatch.delenv("FXENV_CHUNK", raising=False)
+    rng = np.random.default_rng(0)
+    cases = [(4096, 2368, 20), (4096, 2368, 500), (4096, 2368, 1), (64, 2368, 12), (16384, 2368, 300), (5000, 2368, 23),
+             (2369, 2368, 1000), (1, 1, 7)]
+    cases += [(int(rng.integers(1, 40000)), int(rng.integers(1, 4000)), int(rng.integers(1, 3000))) for _ in range(200)]
+    for n_envs, warps, steps in cases:
+        st = plan(n_envs, warps, steps)
+        assert st[0] == 0 and st[-1] == steps and all(b > a for a, b in zip(st, st[1:])), (n_envs, warps, steps, st)
+        lens = [b - a for a, b in zip(st, st[1:])]
+        assert max(lens) <= max(64, steps if n_envs <= warps else 0)
+        if n_envs <= warps:
+            assert lens == [steps]                                  # every env has a warp of its own: one round
+        else:
+            assert len(set(lens[:-1])) <= 1 and lens[-1] <= lens[0]  # uniform rounds, the remainder last and shorter
+            if lens[0] > 1:
+                assert n_envs * len(lens) >= 6 * warps * 0.99 or lens[0] == 64, (n_envs, warps, steps, lens)
+    monkeypatch.setenv("FXENV_CHUNK", "7")
+    assert plan(5000, 2368, 23) == [0, 7, 14, 21, 23]
+    assert plan(64, 2368, 5) == [0, 5]
