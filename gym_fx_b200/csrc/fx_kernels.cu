@@ -37,6 +37,9 @@
 #ifndef FX_LONG_MIN_W
 #define FX_LONG_MIN_W 384  // windows of at least this many rows use the unrolled loop
 #endif
+#ifndef FX_EMIT_INLINE
+#define FX_EMIT_INLINE __forceinline__  // the 16-byte-store row emitter inlined at its call sites: 8.20 vs 8.38 us/step (cfg2)
+#endif
 constexpr int kLongUnroll = FX_LONG_UNROLL;  // (a macro is not expanded inside #pragma unroll)
 #ifndef FX_EMIT_EARLY
 #define FX_EMIT_EARLY 0  // 1: emit the observation windows right after the order sweep (measured: 12.44 vs 12.05 us/step, worse)
@@ -359,11 +362,11 @@ __device__ __noinline__ void fx_emit_windows_t(const FxKernelParams& P, int lane
 // difference is far below half a float32 ulp).  prices | returns: a lane owns 4 consecutive rows.
 // PAD: the episode is younger than the window (s < W rows staged): output row w shows staged row max(0, w - pad), i.e. the
 // first row repeated `pad` times (feature_window_preprocessor.py:153-160,197-204) -- the first W steps of every episode.
-// Not inlined (one copy per kernel, several call sites); what it needs of the configuration arrives BY VALUE: through a
-// reference to the kernel parameters the callee would read them with generic loads (a constant-bank address formed at
-// run time), ~10 dependent round trips at the top of every row.  NOBIN: no binary pass-through feature (LEAN contract).
+// What it needs of the configuration arrives BY VALUE: as a non-inlined function taking a reference to the kernel parameters
+// it read them with generic loads (a constant-bank address formed at run time), ~10 dependent round trips at the top of
+// every row.  (It is now inlined as well, FX_EMIT_INLINE.)  NOBIN: no binary pass-through feature (LEAN contract).
 template <bool CLIP, bool TAME, bool O16, bool PAD, bool LONG, bool NOBIN>
-__device__ __noinline__ void fx_emit_fast5_q(const int lane, const bool scale, const double* __restrict__ win,
+__device__ FX_EMIT_INLINE void fx_emit_fast5_q(const int lane, const bool scale, const double* __restrict__ win,
                                              const double* sstat, float* __restrict__ out, uint16_t* __restrict__ o16_,
                                              const int pad, const int W, const float clipf, const int pc,
                                              const unsigned binary_mask) {
