@@ -21,6 +21,13 @@ def test_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and d["config"]["workload"].startswith("cfg2")
+    # both arms print the SAME config object (bench.common_config), including the episode phase the steps are taken from
+    sys.path.insert(0, ROOT)
+    import bench
+    cfg, _, _, envs, D, _, desc = bench.build_workload("cfg2")
+    pre = bench.preroll_steps(cfg)
+    assert pre > max(cfg.window_size, cfg.scaling_window)
+    assert d["config"] == bench.common_config(desc, envs, D, 1, pre) and "steady state" in d["config"]["episode_phase"]
 
 
 def test_reference_arm_other_ranks_exit_quietly():
